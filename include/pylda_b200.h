@@ -1,0 +1,138 @@
+/*
+ * pylda_b200 -- C ABI of the B200-native variational-Bayes E-step for LDA.
+ *
+ * Drop-in boundary for ONE path of kzhai/PyLDA (reference, pure Python, no FFI of its own):
+ *     variational_bayes.py:132-216   VariationalBayes.e_step
+ *     inferencer.py:15-18            compute_dirichlet_expectation
+ * The reference-side binding (a ctypes stub inside VariationalBayes.e_step) is shown in
+ * INTEGRATION.md; pylda_b200/native.py is that stub, pylda_b200/variational_bayes.py the
+ * class that uses it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every host buffer is caller-owned, C-contiguous, and
+ *     only read/written during the call.  The library owns all device memory, streams,
+ *     events and the NCCL communicator.
+ *   - every function returns 0 on success, non-zero on error; the message is available
+ *     from pylda_last_error().  Nothing is thrown across the ABI.
+ *   - one context per process and GPU (one process per GPU; ranks are joined with
+ *     pylda_comm_init).  Calls on one context must be serialised by the caller.
+ *   - matrices use the REFERENCE's layouts: eta / phi_ss are (K, V) row-major doubles
+ *     (variational_bayes.py:95,147), gamma is (D, K) row-major (variational_bayes.py:150),
+ *     alpha is (K,) (inferencer.py:57).  The (K,V) <-> (V,K) transposition happens on the
+ *     device inside the library.
+ *   - there is no CPU fallback: without a usable CUDA device pylda_create fails.
+ */
+#ifndef PYLDA_B200_H
+#define PYLDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYLDA_ABI_VERSION 1
+#define PYLDA_NCCL_ID_BYTES 128
+
+typedef struct pylda_ctx pylda_ctx;
+
+/* Filled by the E-step entry points (all ranks fill their LOCAL values). */
+typedef struct pylda_stats {
+    int64_t n_docs;            /* documents processed by this context (local shard)          */
+    int64_t nnz;               /* (doc, term) pairs processed                                 */
+    int64_t inner_iters;       /* sum over documents of gamma iterations (:174 loop trips)    */
+    int64_t docs_at_cap;       /* documents that stopped at max_iter instead of converging    */
+    double  prep_ms;           /* E_log_eta producer + table build (inferencer.py:15-18)      */
+    double  kernel_ms;         /* per-document E-step kernels, CUDA-event time on our stream  */
+    double  post_ms;           /* ELBO reduction, transposes, (all-reduce)                    */
+    double  total_ms;          /* device time of the whole call incl. H2D/D2H issued by us    */
+    double  algo_read_bytes;   /* sum_d 8 + 8 n_d + 8 n_d K                     */
+    double  algo_total_bytes;  /* read + sum_d 8 K + 8 n_d K                    */
+    int32_t n_launches;        /* kernels launched by this call                               */
+    int32_t n_estep_launches;  /* of which per-document E-step kernels                        */
+    int64_t docs_resident;     /* documents whose tile was staged in shared memory            */
+    int64_t docs_streamed;     /* documents whose tile was re-streamed from L2/HBM            */
+} pylda_stats;
+
+/* ABI version of the loaded library (== PYLDA_ABI_VERSION of the header it was built from). */
+int pylda_abi_version(void);
+
+/* Create a context on CUDA device `device` (cudaSetDevice ordinal).  Fails (non-zero) when
+ * no sm_100 device is usable.  *out is NULL on failure. */
+int pylda_create(pylda_ctx** out, int device);
+int pylda_destroy(pylda_ctx* ctx);
+
+/* Last error message of `ctx` (or of the failed pylda_create when ctx is NULL).
+ * Owned by the library; valid until the next call on the same context. */
+const char* pylda_last_error(const pylda_ctx* ctx);
+
+/* Upload a parsed corpus (the reference's (word_ids, word_cts) of variational_bayes.py:98-130
+ * packed to CSR: row_ptr[D+1] int64, ids[nnz] int32 term ids unique within a document,
+ * cts[nnz] int32 counts >= 1).  slot 0 = training corpus (self._parsed_corpus),
+ * slot 1 = held-out corpus (the parsed_corpus argument of e_step).  Under multi-GPU every
+ * rank uploads ITS OWN shard of documents.  Copies; the caller may free its arrays. */
+int pylda_set_corpus(pylda_ctx* ctx, int slot, int64_t D, int64_t nnz,
+                     const int64_t* row_ptr, const int32_t* ids, const int32_t* cts);
+
+/* Read the corpus back from the device (token indexing must round-trip bit-exactly). */
+int pylda_get_corpus(pylda_ctx* ctx, int slot, int64_t* row_ptr, int32_t* ids, int32_t* cts);
+
+/* The whole reference call  VariationalBayes.e_step(parsed_corpus, local_parameter_iteration,
+ * local_parameter_converge_threshold)  (variational_bayes.py:132) with HOST buffers:
+ *   eta_KxV, alpha_K     inputs (self._eta, self._alpha_alpha)
+ *   heldout              0: train branch (:212-214), 1: held-out branch (:154-155,:202-204,:216)
+ *   gamma_DxK            out, nullable  (gamma_values)
+ *   phi_ss_KxV           out, nullable  (phi_sufficient_statistics; summed over ranks)
+ *   alpha_ss_K           out, nullable  (sum_d psi(gamma_dk) - psi(sum_k gamma_dk), the alpha
+ *                        statistics m_step needs, variational_bayes.py:232-233; summed over ranks)
+ *   doc_ll               out: document_log_likelihood (:195-199), summed over ranks
+ *   words_ll             out: words_log_likelihood (:204), 0 when heldout == 0
+ * Under multi-GPU (after pylda_comm_init) this is a collective: every rank calls it. */
+int pylda_estep(pylda_ctx* ctx, int slot, int K, int V,
+                const double* eta_KxV, const double* alpha_K,
+                int max_iter, double tol, int heldout,
+                double* gamma_DxK, double* phi_ss_KxV, double* alpha_ss_K,
+                double* doc_ll, double* words_ll, pylda_stats* stats);
+
+/* The same path split so that inputs can stay resident in HBM between calls
+ * (bench.py `value` leg; also what a device-resident M-step feeds):
+ *   pylda_set_model     H2D of eta/alpha into the context
+ *   pylda_estep_resident  E_log_eta producer + E-step kernels + ELBO reduction (+ all-reduce),
+ *                       results stay on the device
+ *   pylda_get_results   D2H of whatever the caller wants (any pointer may be NULL) */
+int pylda_set_model(pylda_ctx* ctx, int K, int V, const double* eta_KxV, const double* alpha_K);
+int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout,
+                         int want_alpha_ss, pylda_stats* stats);
+int pylda_get_results(pylda_ctx* ctx, int slot, double* gamma_DxK, double* phi_ss_KxV,
+                      double* alpha_ss_K, double* doc_ll, double* words_ll, int32_t* iters_D);
+
+/* Device M-step on resident statistics (variational_bayes.py:218-226):
+ * topic_ll from the OLD eta, then eta <- phi_ss + alpha_beta (scalar prior, inferencer.py:58).
+ * eta stays on the device for the next pylda_estep_resident; eta_out_KxV is nullable. */
+int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, double* eta_out_KxV);
+/* Replace alpha on the device (after the host Newton update, variational_bayes.py:277-324). */
+int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K);
+
+/* compute_dirichlet_expectation (inferencer.py:15-18) for a (K,V) matrix on the device.
+ * Exposed for parity tests of the device digamma. */
+int pylda_dirichlet_expectation(pylda_ctx* ctx, int K, int V, const double* eta_KxV, double* out_KxV);
+
+/* Elementwise device special functions used on the path (parity tests against scipy):
+ * which = 0: digamma(x); 1: exp(digamma(x)); 2: lgamma(x). */
+int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double* out);
+
+/* Multi-GPU: one process per GPU.  Rank 0 calls pylda_comm_unique_id, ships the bytes to the
+ * other ranks by any host channel, then every rank calls pylda_comm_init.  Afterwards
+ * pylda_estep / pylda_estep_resident all-reduce (NCCL, sum, f64) the K x V statistics and
+ * the ELBO scalars; gamma stays sharded. */
+int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]);
+int pylda_comm_init(pylda_ctx* ctx, int n_ranks, int rank, const char id[PYLDA_NCCL_ID_BYTES]);
+
+/* Introspection for benches/tests. */
+int pylda_device_name(pylda_ctx* ctx, char* out, int cap);
+int pylda_sm_count(pylda_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYLDA_B200_H */

@@ -1,0 +1,712 @@
+// C ABI of the B200-native VB E-step (include/pylda_b200.h).  Host orchestration only:
+// device memory, streams/events, class scheduling of documents, NCCL (dlopen'd) and the
+// launches of the kernels in estep_kernel.cuh / prep_kernels.cuh.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/pylda_b200.h"
+#include "estep_dispatch.h"
+#include "estep_kernel.cuh"
+#include "prep_kernels.cuh"
+
+using namespace pylda;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- minimal NCCL binding (resolved at pylda_comm_init; single-GPU runs never need it) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[PYLDA_NCCL_ID_BYTES]; } ncclUniqueId;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8, kNcclSum = 0;
+
+bool load_nccl(std::string* err) {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        *err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return false;
+    }
+#define SYM(field, name)                                              \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                        \
+    if (!g_nccl.field) {                                              \
+        *err = std::string("libnccl is missing symbol ") + name;      \
+        return false;                                                 \
+    }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return true;
+}
+
+struct Corpus {
+    long long D = 0, nnz = 0;
+    long long* row_ptr = nullptr;
+    int* ids = nullptr;
+    int* cts = nullptr;
+    int* order = nullptr;            // documents sorted by n_d, longest first
+    std::vector<int> n_sorted;       // host copy of the sorted lengths
+    int max_id = -1;
+    // per-corpus outputs
+    double* gamma = nullptr;
+    size_t gamma_cap = 0;            // doubles
+    double* docterm = nullptr;
+    int* iters = nullptr;
+    bool has_results = false;
+    int results_K = 0;
+};
+
+}  // namespace
+
+struct pylda_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    Corpus corp[2];
+    // model
+    int K = 0, V = 0, KP = 0;
+    double* eta = nullptr;       // (K, V)
+    double* alpha = nullptr;     // (K,)
+    double alpha_max = 0.0, alpha_term = 0.0;
+    std::vector<double> alpha_host;
+    double* Elt = nullptr;       // (V, KP) E_log_eta transposed
+    double* Bt = nullptr;        // (V, KP)
+    double* mw = nullptr;        // (V,)
+    double* phi = nullptr;       // (V, KP) statistics accumulator
+    double* phi_KV = nullptr;    // (K, V) reference layout
+    double* kbuf = nullptr;      // 4*K doubles: psisum, rowsum, lse, rowterm
+    double* alpha_ss = nullptr;  // (K,)
+    double* scal = nullptr;      // 8 doubles
+    double* partial = nullptr;   // reduction scratch
+    size_t partial_cap = 0;
+    int* counters = nullptr;     // class queue heads
+    bool model_set = false;
+    bool phi_KV_valid = false;
+    bool have_alpha_ss = false;
+    double last_scal[8] = {0};
+    // comm
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(pylda_ctx* c, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    if (n == 0) n = 1;
+    return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+void free_corpus(Corpus& c) {
+    cudaFree(c.row_ptr); cudaFree(c.ids); cudaFree(c.cts); cudaFree(c.order);
+    cudaFree(c.gamma); cudaFree(c.docterm); cudaFree(c.iters);
+    c = Corpus();
+}
+
+void free_model(pylda_ctx* c) {
+    cudaFree(c->eta); cudaFree(c->alpha); cudaFree(c->Elt); cudaFree(c->Bt); cudaFree(c->mw);
+    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss);
+    c->eta = c->alpha = c->Elt = c->Bt = c->mw = c->phi = c->phi_KV = c->kbuf = c->alpha_ss = nullptr;
+    c->model_set = false;
+}
+
+// (LK, J) lane shape for K topics: smallest padded width among the compiled shapes.
+bool pick_shape(int K, int* LK, int* J) {
+    const int pairs = (K + 1) / 2;
+    const int Js[] = {5, 7, 8};
+    int best = 1 << 30;
+    bool found = false;
+    for (int lk = 1; lk <= 32; lk <<= 1) {
+        for (int j : Js) {
+            if (lk * j >= pairs && lk * j < best) { best = lk * j; *LK = lk; *J = j; found = true; }
+        }
+    }
+    if (!found && 32 * 16 >= pairs) { *LK = 32; *J = 16; found = true; }
+    return found;
+}
+
+const void* lookup_kernel(int LK, int J, bool res) {
+    switch (LK) {
+        case 1: return estep_kernel_lk1(J, res);
+        case 2: return estep_kernel_lk2(J, res);
+        case 4: return estep_kernel_lk4(J, res);
+        case 8: return estep_kernel_lk8(J, res);
+        case 16: return estep_kernel_lk16(J, res);
+        case 32: return estep_kernel_lk32(J, res);
+    }
+    return nullptr;
+}
+
+// bank-conflict-free shared-memory row stride (doubles) for LDS.128 with LK lanes per row
+int tile_stride(int KP, int LK) {
+    int st = KP;
+    if (LK == 1) { while (st % 4 != 2) st += 2; }
+    else if (LK == 2) { while (st % 8 != 4) st += 2; }
+    else if (LK == 4) { while (st % 16 != 8) st += 2; }
+    return st;
+}
+
+struct GroupLayout {
+    int off_gam, off_spart, off_red, off_cnt, off_mwr, off_rid, off_tile, bytes;
+};
+int align_up(int x, int a) { return (x + a - 1) / a * a; }
+GroupLayout group_layout(int W, int KPAD, int nmax, int ST, bool res) {
+    GroupLayout g;
+    int o = 16;                       // mbarrier + queue slot
+    o += KPAD * 8;                    // es
+    g.off_gam = o;   o += KPAD * 8;
+    g.off_spart = o; o += W * KPAD * 8;
+    g.off_red = o;   o += 16 * 8;
+    g.off_cnt = o;   if (res) o += nmax * 8;
+    g.off_mwr = o;   if (res) o += nmax * 8;
+    g.off_rid = o;   if (res) o += nmax * 4;
+    o = align_up(o, 16);
+    g.off_tile = o;  if (res) o += nmax * ST * 8;
+    g.bytes = align_up(o, 128);
+    return g;
+}
+
+int ensure_partial(pylda_ctx* ctx, size_t n) {
+    if (ctx->partial_cap >= n) return 0;
+    CK(dalloc(&ctx->partial, n));
+    ctx->partial_cap = n;
+    return 0;
+}
+
+int prepare_tables(pylda_ctx* ctx, bool heldout, int* launches) {
+    const int K = ctx->K, V = ctx->V, KP = ctx->KP;
+    double* psisum = ctx->kbuf;
+    k_rowsum_psi<<<K, 256, 0, ctx->stream>>>(ctx->eta, K, V, psisum, ctx->kbuf + K);
+    dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
+    k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(ctx->eta, psisum, K, V, KP, ctx->Elt);
+    const int nb = std::min((V + 7) / 8, ctx->prop.multiProcessorCount * 8);
+    k_build_B<<<nb, 256, 0, ctx->stream>>>(ctx->Elt, K, V, KP, ctx->Bt, ctx->mw, ctx->phi);
+    *launches += 3;
+    if (heldout) {
+        const int nchunk = 64;
+        if (ensure_partial(ctx, (size_t)2 * nchunk * K)) return 1;
+        dim3 lg((K + 31) / 32, nchunk);
+        k_lse_partial<<<lg, 256, 0, ctx->stream>>>(ctx->Elt, K, V, KP, ctx->partial, ctx->partial + (size_t)nchunk * K);
+        k_lse_final<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial, ctx->partial + (size_t)nchunk * K, K, nchunk,
+                                                             ctx->kbuf + 2 * K);
+        *launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
+    const int K = ctx->K, KP = ctx->KP;
+    int LK = 0, J = 0;
+    if (!pick_shape(K, &LK, &J)) return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
+    const int KPAD = 2 * LK * J;
+    const int ST = tile_stride(KP, LK);
+    const int smem_budget = (int)ctx->prop.sharedMemPerBlockOptin;
+    const int cta_fixed = align_up(KPAD * 8, 128);
+    const int Ws[4] = {1, 2, 4, 8};
+    int cap[4];
+    for (int i = 0; i < 4; ++i) {
+        const int W = Ws[i], G = 8 / W;
+        const int avail = ((smem_budget - cta_fixed) / G) & ~127;
+        const GroupLayout g0 = group_layout(W, KPAD, 0, ST, true);
+        int n = (avail - g0.bytes - 128) / (ST * 8 + 20);
+        n &= ~3;
+        cap[i] = std::max(n, 0);
+    }
+    // class boundaries in the length-sorted (descending) order
+    const std::vector<int>& ns = cp.n_sorted;
+    const long long D = cp.D;
+    auto first_leq = [&](int limit) -> long long {   // first index whose n <= limit
+        return std::partition_point(ns.begin(), ns.end(), [&](int n) { return n > limit; }) - ns.begin();
+    };
+    long long b8 = first_leq(cap[3]);   // [0,b8): streaming
+    long long b4 = first_leq(cap[2]);   // [b8,b4): W=8
+    long long b2 = first_leq(cap[1]);   // [b4,b2): W=4
+    long long b1 = first_leq(cap[0]);   // [b2,b1): W=2 ; [b1,D): W=1
+    b4 = std::max(b4, b8); b2 = std::max(b2, b4); b1 = std::max(b1, b2);
+    struct Cls { long long lo, hi; int W; bool res; };
+    const Cls classes[5] = {{0, b8, 8, false}, {b8, b4, 8, true}, {b4, b2, 4, true}, {b2, b1, 2, true}, {b1, D, 1, true}};
+    CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(int), ctx->stream));
+    st->docs_streamed = b8;
+    st->docs_resident = D - b8;
+    for (int ci = 0; ci < 5; ++ci) {
+        const Cls& c = classes[ci];
+        const long long nd = c.hi - c.lo;
+        if (nd <= 0) continue;
+        const void* fn = lookup_kernel(LK, J, c.res);
+        if (!fn) return fail(ctx, "no kernel instantiation for LK=%d J=%d", LK, J);
+        const int G = 8 / c.W;
+        int nmax = 0;
+        if (c.res) nmax = std::max(4, (ns[c.lo] + 3) & ~3);
+        const GroupLayout gl = group_layout(c.W, KPAD, nmax, ST, c.res);
+        const int smem = cta_fixed + G * gl.bytes;
+        if (smem > smem_budget) return fail(ctx, "internal: class %d needs %d B of shared memory", ci, smem);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, smem, 0));
+        if (occ < 1) return fail(ctx, "internal: zero occupancy for class %d (smem %d)", ci, smem);
+        long long grid = (long long)ctx->prop.multiProcessorCount * occ;
+        grid = std::min(grid, (nd + G - 1) / G);
+        EParams p;
+        p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+        p.order = cp.order + c.lo; p.ndocs = (int)nd; p.counter = ctx->counters + ci;
+        p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
+        p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+        p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
+        p.W = c.W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = cta_fixed;
+        p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
+        p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
+        void* args[] = {&p};
+        CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)smem, ctx->stream));
+        st->n_launches++;
+        st->n_estep_launches++;
+    }
+    return 0;
+}
+
+int ensure_outputs(pylda_ctx* ctx, Corpus& cp) {
+    const size_t need = (size_t)cp.D * ctx->K;
+    if (cp.gamma_cap < need || !cp.gamma) {
+        CK(dalloc(&cp.gamma, need));
+        cp.gamma_cap = need;
+    }
+    if (!cp.docterm) CK(dalloc(&cp.docterm, (size_t)cp.D));
+    if (!cp.iters) CK(dalloc(&cp.iters, (size_t)cp.D));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pylda_abi_version(void) { return PYLDA_ABI_VERSION; }
+
+const char* pylda_last_error(const pylda_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int pylda_create(pylda_ctx** out, int device) {
+    pylda_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, "pylda_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, "pylda_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, "pylda_create: device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, "pylda_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx = new pylda_ctx();
+    ctx->device = device;
+    ctx->prop = prop;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete ctx;
+        return 1;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    cudaMalloc((void**)&ctx->scal, 8 * sizeof(double));
+    cudaMemset(ctx->scal, 0, 8 * sizeof(double));
+    cudaMalloc((void**)&ctx->counters, 8 * sizeof(int));
+    *out = ctx;
+    return 0;
+}
+
+int pylda_destroy(pylda_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    free_corpus(ctx->corp[0]);
+    free_corpus(ctx->corp[1]);
+    free_model(ctx);
+    cudaFree(ctx->scal); cudaFree(ctx->partial); cudaFree(ctx->counters);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int pylda_device_name(pylda_ctx* ctx, char* out, int cap) {
+    if (!ctx || !out || cap <= 0) return 1;
+    snprintf(out, cap, "%s", ctx->prop.name);
+    return 0;
+}
+int pylda_sm_count(pylda_ctx* ctx) { return ctx ? ctx->prop.multiProcessorCount : -1; }
+
+int pylda_set_corpus(pylda_ctx* ctx, int slot, int64_t D, int64_t nnz, const int64_t* row_ptr, const int32_t* ids,
+                     const int32_t* cts) {
+    if (!ctx) return 1;
+    if (slot < 0 || slot > 1) return fail(ctx, "pylda_set_corpus: slot must be 0 or 1");
+    if (D < 0 || nnz < 0 || !row_ptr || (nnz > 0 && (!ids || !cts))) return fail(ctx, "pylda_set_corpus: bad arguments");
+    if (D > 0x7fffffffLL) return fail(ctx, "pylda_set_corpus: D=%lld exceeds 2^31-1 documents per GPU", (long long)D);
+    if (row_ptr[0] != 0 || row_ptr[D] != nnz) return fail(ctx, "pylda_set_corpus: row_ptr[0] must be 0 and row_ptr[D] == nnz");
+    int max_n = 0;
+    for (int64_t d = 0; d < D; ++d) {
+        const int64_t n = row_ptr[d + 1] - row_ptr[d];
+        if (n < 0) return fail(ctx, "pylda_set_corpus: row_ptr not monotone at document %lld", (long long)d);
+        if (n > 0x3fffffff) return fail(ctx, "pylda_set_corpus: document %lld too long", (long long)d);
+        max_n = std::max(max_n, (int)n);
+    }
+    int max_id = -1;
+    for (int64_t i = 0; i < nnz; ++i) {
+        if (ids[i] < 0) return fail(ctx, "pylda_set_corpus: negative term id at position %lld", (long long)i);
+        if (cts[i] < 1) return fail(ctx, "pylda_set_corpus: count < 1 at position %lld", (long long)i);
+        max_id = std::max(max_id, ids[i]);
+    }
+    CK(cudaSetDevice(ctx->device));
+    Corpus& cp = ctx->corp[slot];
+    free_corpus(cp);
+    cp.D = D; cp.nnz = nnz; cp.max_id = max_id;
+    // counting sort of documents by length, longest first
+    std::vector<long long> bucket((size_t)max_n + 2, 0);
+    for (int64_t d = 0; d < D; ++d) bucket[(size_t)(max_n - (row_ptr[d + 1] - row_ptr[d])) + 1]++;
+    for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
+    std::vector<int> order((size_t)D);
+    cp.n_sorted.resize((size_t)D);
+    for (int64_t d = 0; d < D; ++d) {
+        const int n = (int)(row_ptr[d + 1] - row_ptr[d]);
+        const long long pos = bucket[(size_t)(max_n - n)]++;
+        order[(size_t)pos] = (int)d;
+        cp.n_sorted[(size_t)pos] = n;
+    }
+    CK(dalloc(&cp.row_ptr, (size_t)D + 1));
+    CK(dalloc(&cp.ids, (size_t)nnz));
+    CK(dalloc(&cp.cts, (size_t)nnz));
+    CK(dalloc(&cp.order, (size_t)D));
+    CK(cudaMemcpyAsync(cp.row_ptr, row_ptr, ((size_t)D + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        CK(cudaMemcpyAsync(cp.ids, ids, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(cp.cts, cts, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (D) CK(cudaMemcpyAsync(cp.order, order.data(), (size_t)D * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pylda_get_corpus(pylda_ctx* ctx, int slot, int64_t* row_ptr, int32_t* ids, int32_t* cts) {
+    if (!ctx) return 1;
+    if (slot < 0 || slot > 1) return fail(ctx, "pylda_get_corpus: slot must be 0 or 1");
+    Corpus& cp = ctx->corp[slot];
+    if (!cp.row_ptr) return fail(ctx, "pylda_get_corpus: slot %d is empty", slot);
+    CK(cudaSetDevice(ctx->device));
+    if (row_ptr) CK(cudaMemcpyAsync(row_ptr, cp.row_ptr, ((size_t)cp.D + 1) * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids && cp.nnz) CK(cudaMemcpyAsync(ids, cp.ids, (size_t)cp.nnz * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cts && cp.nnz) CK(cudaMemcpyAsync(cts, cp.cts, (size_t)cp.nnz * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int set_alpha_host(pylda_ctx* ctx, const double* alpha_K) {
+    const int K = ctx->K;
+    ctx->alpha_host.assign(alpha_K, alpha_K + K);
+    double amax = 0.0, asum = 0.0, lg = 0.0;
+    for (int k = 0; k < K; ++k) {
+        if (!(alpha_K[k] > 0.0) || !isfinite(alpha_K[k])) return fail(ctx, "alpha[%d]=%g must be finite and > 0", k, alpha_K[k]);
+        amax = std::max(amax, alpha_K[k]);
+        asum += alpha_K[k];
+        lg += lgamma(alpha_K[k]);
+    }
+    ctx->alpha_max = amax;
+    ctx->alpha_term = lgamma(asum) - lg;     // variational_bayes.py:195, per document
+    CK(cudaMemcpyAsync(ctx->alpha, alpha_K, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int pylda_set_model(pylda_ctx* ctx, int K, int V, const double* eta_KxV, const double* alpha_K) {
+    if (!ctx) return 1;
+    if (K < 1 || V < 1 || !eta_KxV || !alpha_K) return fail(ctx, "pylda_set_model: bad arguments");
+    int LK, J;
+    if (!pick_shape(K, &LK, &J)) return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
+    CK(cudaSetDevice(ctx->device));
+    if (K != ctx->K || V != ctx->V || !ctx->eta) {
+        free_model(ctx);
+        ctx->K = K; ctx->V = V; ctx->KP = (K + 1) & ~1;
+        const size_t kv = (size_t)K * V, vkp = (size_t)V * ctx->KP;
+        CK(dalloc(&ctx->eta, kv));
+        CK(dalloc(&ctx->alpha, (size_t)K));
+        CK(dalloc(&ctx->Elt, vkp));
+        CK(dalloc(&ctx->Bt, vkp));
+        CK(dalloc(&ctx->mw, (size_t)V));
+        CK(dalloc(&ctx->phi, vkp));
+        CK(dalloc(&ctx->phi_KV, kv));
+        CK(dalloc(&ctx->kbuf, (size_t)4 * K));
+        CK(dalloc(&ctx->alpha_ss, (size_t)K));
+        for (auto& cp : ctx->corp) cp.has_results = false;
+    }
+    CK(cudaMemcpyAsync(ctx->eta, eta_KxV, (size_t)K * V * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (set_alpha_host(ctx, alpha_K)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->model_set = true;
+    return 0;
+}
+
+int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K) {
+    if (!ctx) return 1;
+    if (!ctx->model_set || !alpha_K) return fail(ctx, "pylda_set_alpha: no model on the device");
+    CK(cudaSetDevice(ctx->device));
+    if (set_alpha_host(ctx, alpha_K)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
+                         pylda_stats* stats) {
+    if (!ctx) return 1;
+    if (slot < 0 || slot > 1) return fail(ctx, "pylda_estep: slot must be 0 or 1");
+    if (!ctx->model_set) return fail(ctx, "pylda_estep: no model on the device (pylda_set_model)");
+    Corpus& cp = ctx->corp[slot];
+    if (!cp.row_ptr) return fail(ctx, "pylda_estep: corpus slot %d is empty (pylda_set_corpus)", slot);
+    if (max_iter < 1) return fail(ctx, "pylda_estep: local_parameter_iteration must be >= 1 (got %d)", max_iter);
+    if (cp.max_id >= ctx->V) return fail(ctx, "pylda_estep: corpus has term id %d but V=%d", cp.max_id, ctx->V);
+    CK(cudaSetDevice(ctx->device));
+    pylda_stats st;
+    memset(&st, 0, sizeof st);
+    const int K = ctx->K, V = ctx->V, KP = ctx->KP;
+    if (ensure_outputs(ctx, cp)) return 1;
+    const int nred = ctx->prop.multiProcessorCount * 2;
+    const int nass = ctx->prop.multiProcessorCount * 2;
+    if (ensure_partial(ctx, std::max((size_t)nred * NTERMS, std::max((size_t)nass * K, (size_t)2 * 64 * K)))) return 1;
+
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (prepare_tables(ctx, heldout != 0, &st.n_launches)) return 1;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (launch_estep(ctx, cp, max_iter, tol, &st)) return 1;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    k_reduce_terms<<<nred, 256, 0, ctx->stream>>>(ctx->phi, ctx->Elt, ctx->kbuf + 2 * K, K, V, KP, cp.docterm, cp.iters,
+                                                  cp.D, max_iter, heldout, ctx->partial);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->partial, nred, NTERMS, ctx->scal);
+    st.n_launches += 2;
+    ctx->have_alpha_ss = false;
+    if (want_alpha_ss) {
+        const int warps = 8;
+        if ((size_t)warps * K * sizeof(double) > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_alpha_ss, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * K * (int)sizeof(double)));
+        k_alpha_ss<<<nass, warps * 32, (size_t)warps * K * sizeof(double), ctx->stream>>>(cp.gamma, cp.D, K, ctx->partial);
+        k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->partial, nass, K, ctx->alpha_ss);
+        st.n_launches += 2;
+        ctx->have_alpha_ss = true;
+    }
+    CK(cudaGetLastError());
+    if (ctx->comm) {
+        // [scal5] = local D so that doc_ll can add D_total * alpha_term
+        const double dloc = (double)cp.D;
+        CK(cudaMemcpyAsync(ctx->scal + 5, &dloc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = g_nccl.GroupStart();
+        if (!rc) rc = g_nccl.AllReduce(ctx->phi, ctx->phi, (size_t)V * KP, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+        if (!rc) rc = g_nccl.AllReduce(ctx->scal, ctx->scal, 8, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+        if (!rc && want_alpha_ss)
+            rc = g_nccl.AllReduce(ctx->alpha_ss, ctx->alpha_ss, (size_t)K, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+        const int rc2 = g_nccl.GroupEnd();
+        if (rc || rc2) return fail(ctx, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc ? rc : rc2));
+    }
+    ctx->phi_KV_valid = false;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->last_scal, ctx->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->comm) ctx->last_scal[5] = (double)cp.D;
+    cp.has_results = true;
+    cp.results_K = K;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st.prep_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st.kernel_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st.post_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); st.total_ms = ms;
+    st.n_docs = cp.D;
+    st.nnz = cp.nnz;
+    st.inner_iters = (int64_t)llround(ctx->last_scal[3]);
+    st.docs_at_cap = (int64_t)llround(ctx->last_scal[4]);
+    st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;
+    st.algo_total_bytes = st.algo_read_bytes + 8.0 * (double)cp.D * K + 8.0 * (double)cp.nnz * K;
+    if (stats) *stats = st;
+    return 0;
+}
+
+int pylda_get_results(pylda_ctx* ctx, int slot, double* gamma_DxK, double* phi_ss_KxV, double* alpha_ss_K, double* doc_ll,
+                      double* words_ll, int32_t* iters_D) {
+    if (!ctx) return 1;
+    if (slot < 0 || slot > 1) return fail(ctx, "pylda_get_results: slot must be 0 or 1");
+    Corpus& cp = ctx->corp[slot];
+    if (!cp.has_results) return fail(ctx, "pylda_get_results: no E-step results for slot %d", slot);
+    CK(cudaSetDevice(ctx->device));
+    const int K = ctx->K, V = ctx->V, KP = ctx->KP;
+    if (gamma_DxK && cp.D)
+        CK(cudaMemcpyAsync(gamma_DxK, cp.gamma, (size_t)cp.D * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (phi_ss_KxV) {
+        if (!ctx->phi_KV_valid) {
+            dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
+            k_transpose_VK_to_KV<<<tg, tb, 0, ctx->stream>>>(ctx->phi, K, V, KP, ctx->phi_KV);
+            CK(cudaGetLastError());
+            ctx->phi_KV_valid = true;
+        }
+        CK(cudaMemcpyAsync(phi_ss_KxV, ctx->phi_KV, (size_t)K * V * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (alpha_ss_K) {
+        if (!ctx->have_alpha_ss) return fail(ctx, "pylda_get_results: alpha_ss was not requested in the E-step call");
+        CK(cudaMemcpyAsync(alpha_ss_K, ctx->alpha_ss, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (iters_D && cp.D) CK(cudaMemcpyAsync(iters_D, cp.iters, (size_t)cp.D * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double* s = ctx->last_scal;
+    if (doc_ll) *doc_ll = s[5] * ctx->alpha_term + s[0] - s[1];     // variational_bayes.py:195-199
+    if (words_ll) *words_ll = s[2];                                  // :204
+    return 0;
+}
+
+int pylda_estep(pylda_ctx* ctx, int slot, int K, int V, const double* eta_KxV, const double* alpha_K, int max_iter,
+                double tol, int heldout, double* gamma_DxK, double* phi_ss_KxV, double* alpha_ss_K, double* doc_ll,
+                double* words_ll, pylda_stats* stats) {
+    if (!ctx) return 1;
+    if (pylda_set_model(ctx, K, V, eta_KxV, alpha_K)) return 1;
+    if (pylda_estep_resident(ctx, slot, max_iter, tol, heldout, alpha_ss_K != nullptr, stats)) return 1;
+    return pylda_get_results(ctx, slot, gamma_DxK, phi_ss_KxV, alpha_ss_K, doc_ll, words_ll, nullptr);
+}
+
+int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, double* eta_out_KxV) {
+    if (!ctx) return 1;
+    if (!ctx->model_set) return fail(ctx, "pylda_mstep_resident: no model on the device");
+    if (!ctx->corp[0].has_results) return fail(ctx, "pylda_mstep_resident: run the training E-step first");
+    if (!(alpha_beta > 0.0)) return fail(ctx, "pylda_mstep_resident: alpha_beta must be > 0");
+    CK(cudaSetDevice(ctx->device));
+    const int K = ctx->K, V = ctx->V, KP = ctx->KP;
+    if (!ctx->phi_KV_valid) {
+        dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
+        k_transpose_VK_to_KV<<<tg, tb, 0, ctx->stream>>>(ctx->phi, K, V, KP, ctx->phi_KV);
+        ctx->phi_KV_valid = true;
+    }
+    double* rowterm = ctx->kbuf + 3 * K;
+    k_mstep<<<K, 256, 0, ctx->stream>>>(ctx->eta, ctx->phi_KV, K, V, alpha_beta, rowterm);
+    CK(cudaGetLastError());
+    std::vector<double> rt((size_t)K);
+    CK(cudaMemcpyAsync(rt.data(), rowterm, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (eta_out_KxV)
+        CK(cudaMemcpyAsync(eta_out_KxV, ctx->eta, (size_t)K * V * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // variational_bayes.py:222-224: K*(lgamma(sum alpha_beta) - sum lgamma(alpha_beta)) + sum_k rowterm_k
+    double t = (double)K * (lgamma((double)V * alpha_beta) - (double)V * lgamma(alpha_beta));
+    for (int k = 0; k < K; ++k) t += rt[(size_t)k];
+    if (topic_ll) *topic_ll = t;
+    return 0;
+}
+
+int pylda_dirichlet_expectation(pylda_ctx* ctx, int K, int V, const double* eta_KxV, double* out_KxV) {
+    if (!ctx) return 1;
+    if (K < 1 || V < 1 || !eta_KxV || !out_KxV) return fail(ctx, "pylda_dirichlet_expectation: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    double *eta = nullptr, *ps = nullptr, *elt = nullptr, *out = nullptr;
+    const int KP = (K + 1) & ~1;
+    CK(dalloc(&eta, (size_t)K * V));
+    CK(dalloc(&ps, (size_t)K));
+    CK(dalloc(&elt, (size_t)V * KP));
+    CK(dalloc(&out, (size_t)K * V));
+    CK(cudaMemcpyAsync(eta, eta_KxV, (size_t)K * V * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_rowsum_psi<<<K, 256, 0, ctx->stream>>>(eta, K, V, ps, nullptr);
+    dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
+    k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(eta, ps, K, V, KP, elt);
+    k_transpose_VK_to_KV<<<tg, tb, 0, ctx->stream>>>(elt, K, V, KP, out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_KxV, out, (size_t)K * V * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(eta); cudaFree(ps); cudaFree(elt); cudaFree(out);
+    return 0;
+}
+
+int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double* out) {
+    if (!ctx) return 1;
+    if (which < 0 || which > 2 || n < 0 || (n > 0 && (!x || !out))) return fail(ctx, "pylda_special: bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    double *dx = nullptr, *dy = nullptr;
+    CK(dalloc(&dx, (size_t)n));
+    CK(dalloc(&dy, (size_t)n));
+    CK(cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_special<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(which, n, dx, dy);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dx); cudaFree(dy);
+    return 0;
+}
+
+int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]) {
+    std::string err;
+    if (!load_nccl(&err)) return fail(nullptr, "%s", err.c_str());
+    ncclUniqueId id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return fail(nullptr, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+    memcpy(id_out, id.internal, PYLDA_NCCL_ID_BYTES);
+    return 0;
+}
+
+int pylda_comm_init(pylda_ctx* ctx, int n_ranks, int rank, const char id_in[PYLDA_NCCL_ID_BYTES]) {
+    if (!ctx) return 1;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id_in) return fail(ctx, "pylda_comm_init: bad arguments");
+    std::string err;
+    if (!load_nccl(&err)) return fail(ctx, "%s", err.c_str());
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(id.internal, id_in, PYLDA_NCCL_ID_BYTES);
+    const int rc = g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank);
+    if (rc) { ctx->comm = nullptr; return fail(ctx, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); }
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return 0;
+}
+
+}  // extern "C"

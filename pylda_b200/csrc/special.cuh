@@ -1,0 +1,89 @@
+// fp64 special functions for the VB E-step (sm_100a).
+//
+// The reference evaluates scipy.special.psi (cephes/xsf digamma) at
+// inferencer.py:17-18 and variational_bayes.py:177.  Here both psi(x) and the fused
+// exp(psi(x) - c) are computed branch-free for x > 0:
+//   * recurrence  psi(x) = psi(x+m) - sum_{i<m} 1/(x+i), with the sum folded into ONE
+//     rational Q(x)/P(x), P = prod (x+i), Q = P'  (all terms positive: no cancellation);
+//   * psi(y)      = log y - 1/(2y) - u p(u),      u = 1/y^2,  y = x+6  >= 6
+//   * exp(psi(y)) = z + g(u)/z,                   u = 1/z^2,  z = y - 1/2, y = x+4 >= 4
+//     (so the inner loop needs no log at all);
+//   * a single fp64 division serves both 1/(x+m) and Q/P.
+// p and g are degree-8 near-minimax fits (Chebyshev-node interpolation in 40-digit
+// arithmetic, tools/fit_special.py); measured against mpmath: |psi err| <= 1e-15 max(1,|psi|),
+// exp(psi) relative error <= 3 eps max(1,|psi|) -- the conditioning of exp itself.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pylda {
+
+__device__ __forceinline__ double digamma_pos(double x) {
+    // P = x(x+1)...(x+5), Q = dP/dx
+    double P = x, Q = 1.0;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        const double f = x + (double)i;
+        Q = fma(Q, f, P);
+        P = P * f;
+    }
+    const double y = x + 6.0;
+    const double r = 1.0 / (P * y);
+    const double invy = r * P;
+    const double qp = Q * (r * y);
+    const double u = invy * invy;
+    double p = 0x1.3d3a1cf7d5ce2p+0;
+    p = fma(p, u, -0x1.78afabe0fbee1p-2);
+    p = fma(p, u, 0x1.4d9027aef3165p-4);
+    p = fma(p, u, -0x1.591b310557adfp-6);
+    p = fma(p, u, 0x1.f077969fc7922p-8);
+    p = fma(p, u, -0x1.11110af266f00p-8);
+    p = fma(p, u, 0x1.041040ffe2d6dp-8);
+    p = fma(p, u, -0x1.1111111110839p-7);
+    p = fma(p, u, 0x1.5555555555555p-4);
+    return log(y) - 0.5 * invy - u * p - qp;
+}
+
+// exp(psi(x) + negc) for x > 0.  negc = -c shifts the exponent BEFORE exp is taken so
+// that tiny Dirichlet parameters (psi ~ -1/x) do not underflow against a large c.
+__device__ __forceinline__ double exp_digamma_shifted(double x, double negc) {
+    const double x1 = x + 1.0, x2 = x + 2.0, x3 = x + 3.0;
+    const double a = x * x1, da = x + x1;
+    const double b = x2 * x3, db = x2 + x3;
+    const double P = a * b;
+    const double Q = fma(da, b, a * db);
+    const double z = x + 3.5;
+    const double r = 1.0 / (P * z);
+    const double invz = r * P;
+    const double qp = Q * (r * z);
+    const double u = invz * invz;
+    double g = 0x1.72c2625e26025p-2;
+    g = fma(g, u, -0x1.ab037fd41fbcdp-3);
+    g = fma(g, u, 0x1.16a7995f48852p-4);
+    g = fma(g, u, -0x1.4a0ddd7f70d64p-6);
+    g = fma(g, u, 0x1.e1ae396a755f1p-8);
+    g = fma(g, u, -0x1.0315dff6af42ap-8);
+    g = fma(g, u, 0x1.d1a17ce364565p-9);
+    g = fma(g, u, -0x1.a4fa4f9f36231p-8);
+    g = fma(g, u, 0x1.55555555553dap-5);
+    const double G = fma(invz, g, z);
+    return G * exp(negc - qp);
+}
+
+// cheap stand-in for psi(x), |psi(x) - approx| < 0.12 for all x > 0; only used to pick
+// the per-iteration exponent shift c (any c gives the same phi after normalisation).
+__device__ __forceinline__ double digamma_rough(double x) {
+    return log(x + 0.5) - 1.0 / x;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace pylda

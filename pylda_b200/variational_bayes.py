@@ -1,0 +1,224 @@
+"""Drop-in VariationalBayes (mirror of /root/reference/variational_bayes.py:55-356) whose
+e_step runs on a B200 through the C ABI in include/pylda_b200.h.
+
+What stays host numpy, exactly as in the reference: parse_data (:98-130), m_step (:218-235),
+optimize_hyperparameters (:277-324, including the vector-valued `sum_1_h` quirk at :292),
+export_beta / export_gamma (:326-356).  What moved to the device: everything inside e_step
+(:132-216) including compute_dirichlet_expectation (:152).  There is no CPU fallback: e_step
+raises if the CUDA library or a B200 is missing.
+"""
+import os
+import sys
+import time
+
+import numpy
+import scipy.special
+
+from .inferencer import Inferencer, compute_dirichlet_expectation
+from . import native
+
+
+def pack_parsed_corpus(parsed_corpus):
+    """(word_ids, word_cts) lists of variational_bayes.py:98-130 -> CSR (row_ptr int64,
+    ids int32, cts int32).  Integer work: the token indexing is preserved bit-exactly."""
+    word_ids, word_cts = parsed_corpus
+    assert len(word_ids) == len(word_cts)
+    lengths = numpy.fromiter((len(w) for w in word_ids), dtype=numpy.int64, count=len(word_ids))
+    row_ptr = numpy.zeros(len(word_ids) + 1, dtype=numpy.int64)
+    numpy.cumsum(lengths, out=row_ptr[1:])
+    if len(word_ids):
+        ids = numpy.concatenate([numpy.asarray(w).reshape(-1) for w in word_ids]).astype(numpy.int32)
+        cts = numpy.concatenate([numpy.asarray(c).reshape(-1) for c in word_cts]).astype(numpy.int32)
+    else:
+        ids = numpy.zeros(0, dtype=numpy.int32)
+        cts = numpy.zeros(0, dtype=numpy.int32)
+    assert ids.shape[0] == row_ptr[-1] == cts.shape[0]
+    return row_ptr, ids, cts
+
+
+class VariationalBayes(Inferencer):
+    def __init__(self, hyper_parameter_optimize_interval=1):
+        Inferencer.__init__(self, hyper_parameter_optimize_interval)   # :58-67
+        self._native = None
+        self._train_uploaded = False
+
+    # ---- the object must stay picklable (launch_train.py:203-204): drop the device handle ----
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_native"] = None
+        state["_train_uploaded"] = False
+        return state
+
+    def _context(self):
+        if self._native is None:
+            self._native = native.EStepContext(int(os.environ.get("PYLDA_DEVICE", "0")))
+            self._train_uploaded = False
+        return self._native
+
+    def _initialize(self, corpus, vocab, number_of_topics, alpha_alpha, alpha_beta):
+        # :82-95
+        Inferencer._initialize(self, vocab, number_of_topics, alpha_alpha, alpha_beta)
+        self._parsed_corpus = self.parse_data(corpus)
+        self._number_of_documents = len(self._parsed_corpus[0])
+        self._gamma = numpy.zeros((self._number_of_documents, self._number_of_topics)) \
+            + self._alpha_alpha[numpy.newaxis, :] + 1.0 * self._number_of_types / self._number_of_topics
+        # the only random draw that affects VB results (:95); same global-RNG call as the reference
+        self._eta = numpy.random.gamma(100., 1. / 100., (self._number_of_topics, self._number_of_types))
+        self._train_csr = pack_parsed_corpus(self._parsed_corpus)
+        self._train_uploaded = False
+
+    def parse_data(self, corpus):
+        # :98-130 -- per document: unique in-vocabulary type ids (first-seen order) and counts;
+        # documents with no in-vocabulary token are dropped with a warning.
+        doc_count = 0
+        word_ids, word_cts = [], []
+        lookup = self._type_to_index
+        for document_line in corpus:
+            counts = {}
+            for token in document_line.split():
+                type_id = lookup.get(token)
+                if type_id is None:
+                    continue
+                counts[type_id] = counts.get(type_id, 0) + 1
+            if not counts:
+                sys.stderr.write("warning: document collapsed during parsing")
+                continue
+            word_ids.append(numpy.array(list(counts.keys())))
+            word_cts.append(numpy.array(list(counts.values()))[numpy.newaxis, :])
+            doc_count += 1
+            if doc_count % 10000 == 0:
+                print("successfully parse %d documents..." % doc_count)
+        assert len(word_ids) == len(word_cts)
+        print("successfully parse %d documents..." % doc_count)
+        return (word_ids, word_cts)
+
+    def e_step(self, parsed_corpus=None, local_parameter_iteration=50, local_parameter_converge_threshold=1e-6):
+        """:132-216.  Train branch (parsed_corpus is None): sets self._gamma and returns
+        (document_log_likelihood, phi_sufficient_statistics (K,V)).  Held-out branch: returns
+        (words_log_likelihood, gamma_values) and leaves self._gamma untouched."""
+        ctx = self._context()
+        heldout = parsed_corpus is not None
+        if heldout:
+            word_ids, word_cts = parsed_corpus[0], parsed_corpus[1]
+            assert len(word_ids) == len(word_cts)
+            ctx.set_corpus(1, *pack_parsed_corpus((word_ids, word_cts)))
+            slot, number_of_documents = 1, len(word_ids)
+        else:
+            if not self._train_uploaded:
+                if getattr(self, "_train_csr", None) is None:
+                    self._train_csr = pack_parsed_corpus(self._parsed_corpus)
+                ctx.set_corpus(0, *self._train_csr)
+                self._train_uploaded = True
+            slot, number_of_documents = 0, len(self._parsed_corpus[0])
+        # the reference visits documents in numpy.random.permutation order (:159); the order only
+        # changes fp summation order, but the draw keeps the global RNG stream in step with it
+        numpy.random.permutation(number_of_documents)
+        out = ctx.estep(slot, self._eta, self._alpha_alpha, local_parameter_iteration,
+                        local_parameter_converge_threshold, heldout=heldout,
+                        want_gamma=True, want_phi=not heldout)
+        self._last_estep_stats = out["stats"]
+        if not heldout:
+            self._gamma = out["gamma"]
+            return out["doc_ll"], out["phi_ss"]
+        return out["words_ll"], out["gamma"]
+
+    def m_step(self, phi_sufficient_statistics):
+        # :218-235 -- topic terms from the OLD eta, then eta <- phi_ss + alpha_beta
+        topic_log_likelihood = self._number_of_topics * (
+            scipy.special.gammaln(numpy.sum(self._alpha_beta)) - numpy.sum(scipy.special.gammaln(self._alpha_beta)))
+        topic_log_likelihood += numpy.sum(numpy.sum(scipy.special.gammaln(self._eta), axis=1)
+                                          - scipy.special.gammaln(numpy.sum(self._eta, axis=1)))
+        self._eta = phi_sufficient_statistics + self._alpha_beta
+        assert self._eta.shape == (self._number_of_topics, self._number_of_types)
+        alpha_sufficient_statistics = scipy.special.psi(self._gamma) \
+            - scipy.special.psi(numpy.sum(self._gamma, axis=1)[:, numpy.newaxis])
+        alpha_sufficient_statistics = numpy.sum(alpha_sufficient_statistics, axis=0)
+        return topic_log_likelihood, alpha_sufficient_statistics
+
+    def learning(self):
+        # :239-261
+        self._counter += 1
+        clock_e_step = time.time()
+        document_log_likelihood, phi_sufficient_statistics = self.e_step()
+        clock_e_step = time.time() - clock_e_step
+        clock_m_step = time.time()
+        topic_log_likelihood, alpha_sufficient_statistics = self.m_step(phi_sufficient_statistics)
+        if self._hyper_parameter_optimize_interval > 0 and self._counter % self._hyper_parameter_optimize_interval == 0:
+            self.optimize_hyperparameters(alpha_sufficient_statistics)
+        clock_m_step = time.time() - clock_m_step
+        joint_log_likelihood = document_log_likelihood + topic_log_likelihood
+        print("e_step and m_step of iteration %d finished in %d and %d seconds respectively with log likelihood %g"
+              % (self._counter, clock_e_step, clock_m_step, joint_log_likelihood))
+        return joint_log_likelihood
+
+    def inference(self, corpus):
+        # :263-271
+        parsed_corpus = self.parse_data(corpus)
+        words_log_likelihood, corpus_gamma_values = self.e_step(parsed_corpus)
+        return words_log_likelihood, corpus_gamma_values
+
+    def optimize_hyperparameters(self, alpha_sufficient_statistics, hyper_parameter_iteration=100,
+                                 hyper_parameter_decay_factor=0.9, hyper_parameter_maximum_decay=10,
+                                 hyper_parameter_converge_threshold=1e-6):
+        # :277-324 -- Newton update of the asymmetric alpha (Minka's linear-time form) with step
+        # decay.  NOTE the reference's quirk, kept on purpose so ELBO traces match: `sum_1_h` is
+        # 1/hessian element-wise, NOT summed (:292), so `c` is a K-vector (:295).
+        assert alpha_sufficient_statistics.shape == (self._number_of_topics,)
+        D = self._number_of_documents
+        alpha_update = self._alpha_alpha
+        decay = 0
+        for _ in range(hyper_parameter_iteration):
+            alpha_sum = numpy.sum(self._alpha_alpha)
+            gradient = D * (scipy.special.psi(alpha_sum) - scipy.special.psi(self._alpha_alpha)) \
+                + alpha_sufficient_statistics
+            hessian = -D * scipy.special.polygamma(1, self._alpha_alpha)
+            if numpy.any(numpy.isinf(gradient)) or numpy.any(numpy.isnan(gradient)):
+                print("illegal alpha gradient vector", gradient)
+            sum_g_h = numpy.sum(gradient / hessian)
+            sum_1_h = 1.0 / hessian
+            z = D * scipy.special.polygamma(1, alpha_sum)
+            c = sum_g_h / (1.0 / z + sum_1_h)
+            while True:
+                step_size = numpy.power(hyper_parameter_decay_factor, decay) * (gradient - c) / hessian
+                assert self._alpha_alpha.shape == step_size.shape
+                if numpy.any(self._alpha_alpha <= step_size):
+                    decay += 1
+                    if decay > hyper_parameter_maximum_decay:
+                        break
+                else:
+                    alpha_update = self._alpha_alpha - step_size
+                    break
+            mean_change = numpy.mean(abs(alpha_update - self._alpha_alpha))
+            self._alpha_alpha = alpha_update
+            if mean_change <= hyper_parameter_converge_threshold:
+                break
+        return
+
+    def export_beta(self, exp_beta_path, top_display=-1):
+        # :326-341
+        E_log_eta = compute_dirichlet_expectation(self._eta)
+        with open(exp_beta_path, 'w') as output:
+            for topic_index in range(self._number_of_topics):
+                output.write("==========\t%d\t==========\n" % topic_index)
+                row = E_log_eta[topic_index, :]
+                beta_probability = numpy.exp(row - scipy.special.logsumexp(row))
+                for rank, type_index in enumerate(reversed(numpy.argsort(beta_probability)), 1):
+                    output.write("%s\t%g\n" % (self._index_to_type[type_index], beta_probability[type_index]))
+                    if top_display > 0 and rank >= top_display:
+                        break
+
+    def export_gamma(self, exp_gamma_path, top_display=-1):
+        # :343-356
+        exp_gamma = self._gamma / numpy.sum(self._gamma, axis=1)[:, numpy.newaxis]
+        with open(exp_gamma_path, 'w') as output:
+            for document_index in range(self._number_of_documents):
+                fields = []
+                for rank, topic_index in enumerate(reversed(numpy.argsort(exp_gamma[document_index, :])), 1):
+                    fields.append("%d:%g" % (topic_index, exp_gamma[document_index, topic_index]))
+                    if top_display > 0 and rank >= top_display:
+                        break
+                output.write("%s\n" % "\t".join(fields))
+
+
+if __name__ == "__main__":
+    print("not implemented...")

@@ -1,0 +1,145 @@
+"""GPU parity tests proper: CUDA path through the C ABI vs (a) fixtures generated from the
+reference itself and (b) the oracle on seeded inputs.  Tolerance: 1e-5 relative (north_star)."""
+import numpy
+import pytest
+
+from tests.util import CASES, PHI_FLOOR, RTOL, load_golden, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(out, ref_gamma, ref_phi, ref_doc_ll, tag):
+    eg = max_rel(out["gamma"], ref_gamma)
+    ep = max_rel(out["phi_ss"], ref_phi, floor=PHI_FLOOR)
+    el = abs(out["doc_ll"] - ref_doc_ll) / abs(ref_doc_ll)
+    print("%s: gamma %.2e phi_ss %.2e doc_ll %.2e" % (tag, eg, ep, el))
+    assert eg <= RTOL, (tag, "gamma", eg)
+    assert ep <= RTOL, (tag, "phi_ss", ep)
+    assert el <= RTOL, (tag, "doc_ll", el)
+    return eg, ep, el
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_train_branch(ctx, name):
+    g = load_golden(name)
+    ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
+    out = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6)
+    _check(out, g["gamma"], g["phi_ss"], g["doc_ll"], name)
+    # invariants: each phi row sums to 1
+    N = numpy.add.reduceat(g["cts"].astype(numpy.float64), g["row_ptr"][:-1])
+    assert numpy.allclose(out["gamma"].sum(axis=1), g["alpha"].sum() + N, rtol=1e-12)
+    assert abs(out["phi_ss"].sum() - g["cts"].sum()) <= 1e-9 * g["cts"].sum()
+
+
+def test_golden_heldout_branch(ctx):
+    g = load_golden("ap200_k10")
+    ctx.set_corpus(1, g["h_row_ptr"], g["h_ids"], g["h_cts"])
+    out = ctx.estep(1, g["eta"], g["alpha"], 50, 1e-6, heldout=True, want_phi=False)
+    eg = max_rel(out["gamma"], g["h_gamma"])
+    el = abs(out["words_ll"] - float(g["h_words_ll"])) / abs(float(g["h_words_ll"]))
+    print("heldout: gamma %.2e words_ll %.2e" % (eg, el))
+    assert eg <= RTOL and el <= RTOL
+
+
+def test_corpus_roundtrip_bit_exact(ctx):
+    g = load_golden("zipf48_k100")
+    ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
+    r, i, c = ctx.get_corpus(0)
+    assert numpy.array_equal(r, g["row_ptr"]) and numpy.array_equal(i, g["ids"]) and numpy.array_equal(c, g["cts"])
+
+
+@pytest.mark.parametrize("K,V,D,length", [
+    (3, 50, 40, "poisson"), (10, 300, 64, "poisson"), (16, 300, 64, "zipf"), (25, 400, 48, "poisson"),
+    (50, 2000, 64, "zipf"), (64, 500, 32, "poisson"), (100, 5000, 96, "zipf"), (128, 800, 24, "poisson"),
+    (200, 1500, 24, "zipf"), (500, 3000, 12, "poisson"), (501, 1200, 6, "poisson"), (1000, 1500, 4, "poisson"),
+])
+def test_against_oracle_shapes(ctx, K, V, D, length):
+    """Every lane shape (LK,J), every group size class and the streaming path (zipf lengths reach
+    documents whose tile does not fit in shared memory for the larger K)."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    row_ptr, ids, cts = synthetic.synthetic_corpus(D, V, seed=77 + K, length=length, mean_len=60)
+    eta = synthetic.initial_eta(K, V, seed=K)
+    rs = numpy.random.RandomState(K)
+    alpha = rs.uniform(0.02, 0.5, K) if K % 2 else numpy.full(K, 1.0 / K)
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6, heldout=True, return_iters=True)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6, heldout=True)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "K=%d" % K)
+    assert abs(out["words_ll"] - ref["words_ll"]) <= RTOL * abs(ref["words_ll"])
+    res = ctx.get_results(0, gamma=False, phi=False, iters=True)
+    assert numpy.array_equal(res["iters"], ref["iters"])
+    print("stats", out["stats"])
+
+
+def test_warm_model_early_exit(ctx):
+    """After a few EM iterations documents converge before the cap: trip counts must match the oracle's."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 20, 600
+    row_ptr, ids, cts = synthetic.synthetic_corpus(80, V, seed=5, length="poisson", mean_len=80)
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    ab = numpy.full(V, 1.0 / V)
+    trace, eta_w, alpha_w, _ = O.learning_trace(row_ptr, ids, cts, eta, alpha, ab, 4)
+    ref = O.e_step(row_ptr, ids, cts, eta_w, alpha_w, return_iters=True)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta_w, alpha_w)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "warm")
+    it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    assert (ref["iters"] < 50).any()
+    assert numpy.mean(it == ref["iters"]) >= 0.98   # a borderline |d gamma| == tol document may flip by one trip
+
+
+def test_max_iter_and_tol_arguments(ctx):
+    from oracle import estep_oracle as O
+    g = load_golden("syn96_k50")
+    ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
+    for max_iter, tol in ((1, 1e-6), (7, 1e-6), (50, 1e-2)):
+        ref = O.e_step(g["row_ptr"], g["ids"], g["cts"], g["eta"], g["alpha"], max_iter, tol)
+        out = ctx.estep(0, g["eta"], g["alpha"], max_iter, tol)
+        _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "max_iter=%d tol=%g" % (max_iter, tol))
+
+
+def test_special_functions_vs_scipy(ctx):
+    import scipy.special as sp
+    rs = numpy.random.RandomState(1)
+    x = numpy.concatenate([10 ** rs.uniform(-6, 7, 200000), rs.uniform(0, 12, 100000), [1e-6, 1.0, 2.0, 1e7]])
+    psi = ctx.special("digamma", x)
+    ref = sp.psi(x)
+    err = numpy.abs(psi - ref) / numpy.maximum(1.0, numpy.abs(ref))
+    print("digamma max err", err.max())
+    assert err.max() <= 1e-13
+    ex = ctx.special("exp_digamma", x)
+    refe = numpy.exp(ref)
+    ok = refe > 1e-290
+    erre = numpy.abs(ex[ok] - refe[ok]) / refe[ok] / numpy.maximum(1.0, numpy.abs(ref[ok]))
+    print("exp(digamma) max err / cond", erre.max())
+    assert erre.max() <= 1e-13
+    lg = ctx.special("lgamma", x)
+    refl = sp.gammaln(x)
+    errl = numpy.abs(lg - refl) / numpy.maximum(1.0, numpy.abs(refl))
+    assert errl.max() <= 1e-13
+
+
+def test_dirichlet_expectation_vs_oracle(ctx):
+    from oracle import estep_oracle as O
+    rs = numpy.random.RandomState(3)
+    eta = numpy.concatenate([rs.gamma(100., 0.01, (7, 900)), rs.gamma(0.01, 1.0, (7, 900)) + 1e-4], axis=0)
+    out = ctx.dirichlet_expectation(eta)
+    ref = O.compute_dirichlet_expectation(eta)
+    assert max_rel(out, ref, floor=1.0) <= 1e-12
+
+
+def test_error_behaviour(ctx):
+    g = load_golden("syn96_k50")
+    ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
+    with pytest.raises(RuntimeError):
+        ctx.estep(0, g["eta"][:, :10], g["alpha"])            # V smaller than the largest term id
+    with pytest.raises(RuntimeError):
+        ctx.estep(0, g["eta"], g["alpha"], max_iter=0)
+    with pytest.raises(RuntimeError):
+        bad = g["alpha"].copy(); bad[0] = -1.0
+        ctx.estep(0, g["eta"], bad)
+    with pytest.raises(RuntimeError):
+        ctx.set_corpus(0, g["row_ptr"], g["ids"], numpy.zeros_like(g["cts"]))   # counts must be >= 1
