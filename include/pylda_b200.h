@@ -128,6 +128,11 @@ int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double*
 int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]);
 int pylda_comm_init(pylda_ctx* ctx, int n_ranks, int rank, const char id[PYLDA_NCCL_ID_BYTES]);
 
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) so that the H2D/D2H copies of
+ * pylda_estep run at full PCIe rate.  Optional: pageable buffers work, only slower. */
+int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes);
+int pylda_host_unregister(pylda_ctx* ctx, void* ptr);
+
 /* Introspection for benches/tests. */
 int pylda_device_name(pylda_ctx* ctx, char* out, int cap);
 int pylda_sm_count(pylda_ctx* ctx);

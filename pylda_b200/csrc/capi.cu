@@ -683,6 +683,20 @@ int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double*
     return 0;
 }
 
+int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes) {
+    if (!ctx) return 1;
+    if (!ptr || bytes <= 0) return fail(ctx, "pylda_host_register: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int pylda_host_unregister(pylda_ctx* ctx, void* ptr) {
+    if (!ctx) return 1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(ptr));
+    return 0;
+}
+
 int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]) {
     std::string err;
     if (!load_nccl(&err)) return fail(nullptr, "%s", err.c_str());

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "pylda_special": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, _c_double_p, _c_double_p]),
     "pylda_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "pylda_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "pylda_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "pylda_host_unregister": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "pylda_device_name": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "pylda_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
 }
@@ -159,13 +161,18 @@ class EStepContext(object):
 
     # -- the reference call: e_step with host buffers ----------------------------------------
     def estep(self, slot, eta, alpha, max_iter=50, tol=1e-6, heldout=False,
-              want_gamma=True, want_phi=True, want_alpha_ss=False):
+              want_gamma=True, want_phi=True, want_alpha_ss=False, gamma_out=None, phi_out=None):
         eta = numpy.ascontiguousarray(eta, dtype=numpy.float64)
         K, V = eta.shape
         alpha = _checked(alpha, numpy.float64, (K,), "alpha")
         D, _ = self._corpus_dims[slot]
-        gamma = numpy.empty((D, K), dtype=numpy.float64) if want_gamma else None
-        phi = numpy.empty((K, V), dtype=numpy.float64) if want_phi else None
+        gamma = phi = None
+        if want_gamma:
+            gamma = numpy.empty((D, K), dtype=numpy.float64) if gamma_out is None else gamma_out
+            assert gamma.shape == (D, K) and gamma.dtype == numpy.float64 and gamma.flags.c_contiguous
+        if want_phi:
+            phi = numpy.empty((K, V), dtype=numpy.float64) if phi_out is None else phi_out
+            assert phi.shape == (K, V) and phi.dtype == numpy.float64 and phi.flags.c_contiguous
         ass = numpy.empty(K, dtype=numpy.float64) if want_alpha_ss else None
         doc_ll = ctypes.c_double(0.0)
         words_ll = ctypes.c_double(0.0)
@@ -249,6 +256,15 @@ class EStepContext(object):
     def comm_init(self, n_ranks, rank, unique_id):
         assert len(unique_id) == NCCL_ID_BYTES
         self._check(self._lib.pylda_comm_init(self._h, int(n_ranks), int(rank), unique_id), "pylda_comm_init")
+
+    def pin(self, array):
+        """Page-lock a numpy array in place (cudaHostRegister)."""
+        self._check(self._lib.pylda_host_register(self._h, ctypes.c_void_p(array.ctypes.data), array.nbytes),
+                    "pylda_host_register")
+
+    def unpin(self, array):
+        self._check(self._lib.pylda_host_unregister(self._h, ctypes.c_void_p(array.ctypes.data)),
+                    "pylda_host_unregister")
 
     def device_name(self):
         buf = ctypes.create_string_buffer(256)
