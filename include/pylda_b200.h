@@ -118,7 +118,8 @@ int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K);
 int pylda_dirichlet_expectation(pylda_ctx* ctx, int K, int V, const double* eta_KxV, double* out_KxV);
 
 /* Elementwise device special functions used on the path (parity tests against scipy):
- * which = 0: digamma(x); 1: exp(digamma(x)); 2: lgamma(x). */
+ * which = 0: digamma(x); 1: exp(digamma(x)) (shifted form, c = 0); 2: lgamma(x); 3: Newton reciprocal
+ * 1/x; 4: exp(digamma(x)) as the second-generation kernel evaluates it. */
 int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double* out);
 
 /* Multi-GPU: one process per GPU.  Rank 0 calls pylda_comm_unique_id, ships the bytes to the

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -162,8 +163,19 @@ void free_model(pylda_ctx* c) {
 }
 
 // (LK, J) lane shape for K topics: smallest padded width among the compiled shapes.
-bool pick_shape(int K, int* LK, int* J) {
+// v2 adds (4, 13) (K = 100 -> 104 padded columns instead of 112); PYLDA_SHAPE="LK,J" forces a shape.
+bool pick_shape(int K, int* LK, int* J, bool v2 = false) {
     const int pairs = (K + 1) / 2;
+    if (v2) {
+        const char* env = getenv("PYLDA_SHAPE");
+        int lk = 0, j = 0;
+        if (env && sscanf(env, "%d,%d", &lk, &j) == 2 && lk * j >= pairs &&
+            (((lk == 1 || lk == 2 || lk == 4 || lk == 8 || lk == 16 || lk == 32) && (j == 5 || j == 7 || j == 8)) ||
+             (lk == 4 && j == 13) || (lk == 32 && j == 16))) {
+            *LK = lk; *J = j;
+            return true;
+        }
+    }
     const int Js[] = {5, 7, 8};
     int best = 1 << 30;
     bool found = false;
@@ -172,6 +184,7 @@ bool pick_shape(int K, int* LK, int* J) {
             if (lk * j >= pairs && lk * j < best) { best = lk * j; *LK = lk; *J = j; found = true; }
         }
     }
+    if (v2 && 4 * 13 >= pairs && 4 * 13 < best) { best = 52; *LK = 4; *J = 13; found = true; }
     if (!found && 32 * 16 >= pairs) { *LK = 32; *J = 16; found = true; }
     return found;
 }
@@ -184,6 +197,30 @@ const void* lookup_kernel(int LK, int J, bool res) {
         case 8: return estep_kernel_lk8(J, res);
         case 16: return estep_kernel_lk16(J, res);
         case 32: return estep_kernel_lk32(J, res);
+    }
+    return nullptr;
+}
+
+const void* lookup_v2(int LK, int J, int W) {
+    switch (LK) {
+        case 1: return estep_v2_lk1(J, W);
+        case 2: return estep_v2_lk2(J, W);
+        case 4: return estep_v2_lk4(J, W);
+        case 8: return estep_v2_lk8(J, W);
+        case 16: return estep_v2_lk16(J, W);
+        case 32: return estep_v2_lk32(J, W);
+    }
+    return nullptr;
+}
+
+const void* lookup_rt(int LK, int J, int W, int* R) {
+    switch (LK) {
+        case 1: return estep_rt_lk1(J, W, R);
+        case 2: return estep_rt_lk2(J, W, R);
+        case 4: return estep_rt_lk4(J, W, R);
+        case 8: return estep_rt_lk8(J, W, R);
+        case 16: return estep_rt_lk16(J, W, R);
+        case 32: return estep_rt_lk32(J, W, R);
     }
     return nullptr;
 }
@@ -217,6 +254,46 @@ GroupLayout group_layout(int W, int KPAD, int nmax, int ST, bool res) {
     return g;
 }
 
+// shared-memory layout of one document group of estep_v2 (W warps)
+GroupLayout group_layout_v2(int W, int LK, int KPAD, int nmax, int ST) {
+    GroupLayout g;
+    const int LN = 32 / LK;
+    const int NP = (W >= 4) ? W : W * LN;
+    int o = 16;                       // mbarrier + queue slot
+    o += KPAD * 8;                    // es
+    g.off_gam = 0;
+    g.off_spart = o; o += NP * KPAD * 8;
+    g.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    g.off_cnt = o;   o += nmax * 8;
+    g.off_mwr = o;   o += nmax * 8;
+    g.off_rid = o;   o += nmax * 4;
+    o = align_up(o, 16);
+    g.off_tile = o;  o += nmax * ST * 8 + KPAD * 8;   // + slack for the unpredicated over-read of the last row
+    g.bytes = align_up(o, 128);
+    return g;
+}
+
+// shared-memory layout of one document group of estep_rt (W warps, cap = W * LN * R rows)
+GroupLayout group_layout_rt(int W, int LK, int KPAD, int cap, int ST) {
+    GroupLayout g;
+    const int LN = 32 / LK;
+    const int WL = W * LN;
+    const int NB = WL > 64 ? 3 : WL > 32 ? 2 : WL > 16 ? 1 : 0;
+    const int NP = WL >> NB;
+    int o = 16;                       // mbarrier + queue slot
+    o += 2 * KPAD * 8;                // e, double buffered
+    g.off_gam = 0;
+    g.off_spart = o; o += NP * KPAD * 8;
+    g.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    g.off_cnt = o;   o += cap * 8;
+    g.off_mwr = o;   o += cap * 8;
+    g.off_rid = o;   o += cap * 4;
+    o = align_up(o, 16);
+    g.off_tile = o;  o += cap * ST * 8 + KPAD * 8;
+    g.bytes = align_up(o, 128);
+    return g;
+}
+
 int ensure_partial(pylda_ctx* ctx, size_t n) {
     if (ctx->partial_cap >= n) return 0;
     CK(dalloc(&ctx->partial, n));
@@ -246,7 +323,7 @@ int prepare_tables(pylda_ctx* ctx, bool heldout, int* launches) {
     return 0;
 }
 
-int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
+int launch_estep_v1(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
     const int K = ctx->K, KP = ctx->KP;
     int LK = 0, J = 0;
     if (!pick_shape(K, &LK, &J)) return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
@@ -315,6 +392,201 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     return 0;
 }
 
+// Length classes of the resident path: documents are sorted by n_d (descending) and each class
+// (W warps per document, at most G documents in flight per CTA) takes the documents whose tile
+// fits its per-group share of shared memory but not the next class's.  Default "8x1,4x2,2x4,1x8";
+// PYLDA_CLASSES overrides it for tuning (e.g. "8x1,4x2,2x4,2x8,1x8"), PYLDA_KERNEL=v1 selects the
+// first-generation kernel.
+struct ClassCfg { int W, G; };
+
+std::vector<ClassCfg> class_config(int KPAD) {
+    std::vector<ClassCfg> out;
+    const char* env = getenv("PYLDA_CLASSES");
+    std::string spec = env && *env ? env : "8x1,4x2,2x4,1x8";
+    size_t pos = 0;
+    while (pos < spec.size()) {
+        size_t end = spec.find(',', pos);
+        if (end == std::string::npos) end = spec.size();
+        int W = 0, G = 0;
+        if (sscanf(spec.substr(pos, end - pos).c_str(), "%dx%d", &W, &G) == 2 &&
+            (W == 1 || W == 2 || W == 4 || W == 8) && G >= 1 && W * G <= 8 && KPAD <= 128 * W)
+            out.push_back({W, G});
+        pos = end + 1;
+    }
+    if (out.empty()) out = {{8, 1}};
+    return out;
+}
+
+// PYLDA_PROFILE_CLASSES=1: CUDA-event time of every class launch, printed to stderr (tuning aid)
+struct ClassTimer {
+    struct Rec { cudaEvent_t a, b; std::string tag; };
+    std::vector<Rec> recs;
+    bool on = getenv("PYLDA_PROFILE_CLASSES") != nullptr;
+    void begin(cudaStream_t s, const char* fmt, ...) {
+        if (!on) return;
+        char buf[256];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        Rec r; cudaEventCreate(&r.a); cudaEventCreate(&r.b); r.tag = buf;
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) { if (on) cudaEventRecord(recs.back().b, s); }
+    void report(cudaStream_t s) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        for (auto& r : recs) {
+            float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+            fprintf(stderr, "[pylda class] %-60s %9.3f ms\n", r.tag.c_str(), ms);
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        recs.clear();
+    }
+};
+
+int launch_streaming(pylda_ctx* ctx, Corpus& cp, long long nd, int LK, int J, int max_iter, double tol, pylda_stats* st,
+                     int counter_slot) {
+    const int K = ctx->K, KP = ctx->KP;
+    const int KPAD = 2 * LK * J;
+    const int ST = tile_stride(KP, LK);
+    const void* fn = lookup_kernel(LK, J, false);
+    if (!fn) return fail(ctx, "no kernel instantiation for LK=%d J=%d", LK, J);
+    const int cta_fixed = align_up(KPAD * 8, 128);
+    const GroupLayout gl = group_layout(8, KPAD, 0, ST, false);
+    const int smem = cta_fixed + gl.bytes;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, smem, 0));
+    if (occ < 1) return fail(ctx, "internal: zero occupancy for the streaming class (smem %d)", smem);
+    long long grid = std::min<long long>((long long)ctx->prop.multiProcessorCount * occ, nd);
+    EParams p;
+    memset(&p, 0, sizeof p);
+    p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+    p.order = cp.order; p.ndocs = (int)nd; p.counter = ctx->counters + counter_slot;
+    p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
+    p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+    p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
+    p.W = 8; p.nmax = 0; p.group_bytes = gl.bytes; p.off_groups = cta_fixed;
+    p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
+    p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
+    void* args[] = {&p};
+    CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)smem, ctx->stream));
+    st->n_launches++;
+    st->n_estep_launches++;
+    return 0;
+}
+
+int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
+    const int K = ctx->K, KP = ctx->KP;
+    int LK = 0, J = 0, LK1 = 0, J1 = 0;
+    if (!pick_shape(K, &LK, &J, true) || !pick_shape(K, &LK1, &J1, false))
+        return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
+    const int KPAD = 2 * LK * J;
+    const int LN = 32 / LK;
+    const int ST = KP;                                     // rows packed (LDS.128 over LK lanes is conflict-free per quarter warp)
+    const int smem_budget = (int)ctx->prop.sharedMemPerBlockOptin;
+    const char* kv = getenv("PYLDA_KERNEL");
+    const bool use_rt = !(kv && !strcmp(kv, "v2"));
+
+    // Candidate classes, each with a row capacity; a document goes to the class with the smallest
+    // capacity that holds it.  kind 0 = estep_v2 (tile in shared memory), kind 1 = estep_rt (tile
+    // in registers); documents above every capacity use the streaming kernel.
+    struct Cls { int kind, W, G, cap; const void* fn; long long lo, hi; };
+    std::vector<Cls> cls;
+    for (const ClassCfg& c : class_config(KPAD)) {
+        const int avail = (smem_budget / c.G) & ~127;
+        const GroupLayout g0 = group_layout_v2(c.W, LK, KPAD, 0, ST);
+        int n = (avail - g0.bytes - 128) / (ST * 8 + 20);
+        n = n / LN * LN;
+        const void* fn = lookup_v2(LK, J, c.W);
+        if (n > 0 && fn) cls.push_back({0, c.W, c.G, n, fn, 0, 0});
+    }
+    if (use_rt) {
+        for (int W = 8; W >= 1; W >>= 1) {
+            int R = 0;
+            const void* fn = lookup_rt(LK, J, W, &R);
+            if (!fn) continue;
+            const int cap = W * LN * R;
+            const GroupLayout gl = group_layout_rt(W, LK, KPAD, cap, ST);
+            if ((8 / W) * gl.bytes > smem_budget) continue;
+            // drop v2 classes that the register-tile class makes redundant (not larger, not fewer warps per row)
+            cls.erase(std::remove_if(cls.begin(), cls.end(), [&](const Cls& c) { return c.kind == 0 && c.cap <= cap; }),
+                      cls.end());
+            cls.push_back({1, W, 8 / W, cap, fn, 0, 0});
+        }
+    }
+    std::sort(cls.begin(), cls.end(), [](const Cls& a, const Cls& b) { return a.cap > b.cap; });
+    // equal capacities: keep the first
+    cls.erase(std::unique(cls.begin(), cls.end(), [](const Cls& a, const Cls& b) { return a.cap == b.cap; }), cls.end());
+    const int NC = (int)cls.size();
+    if (NC + 1 > 16) return fail(ctx, "too many length classes");
+
+    const std::vector<int>& ns = cp.n_sorted;
+    const long long D = cp.D;
+    auto first_leq = [&](int limit) -> long long {   // first index (descending order) whose n <= limit
+        return std::partition_point(ns.begin(), ns.end(), [&](int n) { return n > limit; }) - ns.begin();
+    };
+    CK(cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(int), ctx->stream));
+    for (int i = 0; i < NC; ++i) cls[i].lo = first_leq(cls[i].cap);
+    for (int i = 0; i < NC; ++i) cls[i].hi = (i + 1 < NC) ? cls[i + 1].lo : D;
+    const long long nstream = NC ? cls[0].lo : D;
+    st->docs_streamed = nstream;
+    st->docs_resident = D - nstream;
+    ClassTimer timer;
+    if (nstream > 0) {
+        timer.begin(ctx->stream, "streaming docs=%lld nmax=%d", nstream, ns[0]);
+        if (launch_streaming(ctx, cp, nstream, LK1, J1, max_iter, tol, st, 0)) return 1;
+        timer.end(ctx->stream);
+    }
+    for (int ci = 0; ci < NC; ++ci) {
+        const Cls& c = cls[ci];
+        const long long nd = c.hi - c.lo;
+        if (nd <= 0) continue;
+        const int W = c.W;
+        int nmax, G;
+        GroupLayout gl;
+        if (c.kind == 1) {
+            nmax = c.cap;
+            gl = group_layout_rt(W, LK, KPAD, c.cap, ST);
+            G = 8 / W;
+        } else {
+            nmax = std::max(LN, (ns[c.lo] + LN - 1) / LN * LN);
+            gl = group_layout_v2(W, LK, KPAD, nmax, ST);
+            // shorter documents than the class limit: pack more groups per CTA, up to the thread bound
+            G = std::min(8 / W, smem_budget / gl.bytes);
+            if (getenv("PYLDA_FIXED_G")) G = std::min(G, c.G);
+        }
+        if (G < 1) return fail(ctx, "internal: class %d needs %d B of shared memory per group", ci, gl.bytes);
+        G = (int)std::min<long long>(G, nd);
+        const int smem = G * gl.bytes;
+        const int threads = G * W * 32;
+        CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, c.fn, threads, smem, 0));
+        if (occ < 1) return fail(ctx, "internal: zero occupancy for class %d (smem %d, threads %d)", ci, smem, threads);
+        long long grid = (long long)ctx->prop.multiProcessorCount * occ;
+        grid = std::min(grid, (nd + G - 1) / G);
+        EParams p;
+        memset(&p, 0, sizeof p);
+        p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+        p.order = cp.order + c.lo; p.ndocs = (int)nd; p.counter = ctx->counters + 1 + ci;
+        p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
+        p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+        p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
+        p.W = W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = 0;
+        p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
+        p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
+        void* args[] = {&p};
+        timer.begin(ctx->stream, "%s W=%d G=%d docs=%lld nmax=%d nmin=%d smem=%d grid=%lld", c.kind ? "rt" : "v2", W, G, nd,
+                    ns[c.lo], ns[c.hi - 1], smem, grid);
+        CK(cudaLaunchKernel(c.fn, dim3((unsigned)grid), dim3(threads), args, (size_t)smem, ctx->stream));
+        timer.end(ctx->stream);
+        st->n_launches++;
+        st->n_estep_launches++;
+    }
+    timer.report(ctx->stream);
+    return 0;
+}
+
 int ensure_outputs(pylda_ctx* ctx, Corpus& cp) {
     const size_t need = (size_t)cp.D * ctx->K;
     if (cp.gamma_cap < need || !cp.gamma) {
@@ -362,7 +634,7 @@ int pylda_create(pylda_ctx** out, int device) {
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     cudaMalloc((void**)&ctx->scal, 8 * sizeof(double));
     cudaMemset(ctx->scal, 0, 8 * sizeof(double));
-    cudaMalloc((void**)&ctx->counters, 8 * sizeof(int));
+    cudaMalloc((void**)&ctx->counters, 16 * sizeof(int));
     *out = ctx;
     return 0;
 }
@@ -526,7 +798,12 @@ int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (prepare_tables(ctx, heldout != 0, &st.n_launches)) return 1;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (launch_estep(ctx, cp, max_iter, tol, &st)) return 1;
+    {
+        const char* kv = getenv("PYLDA_KERNEL");
+        const int rc = (kv && !strcmp(kv, "v1")) ? launch_estep_v1(ctx, cp, max_iter, tol, &st)
+                                                 : launch_estep(ctx, cp, max_iter, tol, &st);
+        if (rc) return 1;
+    }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     k_reduce_terms<<<nred, 256, 0, ctx->stream>>>(ctx->phi, ctx->Elt, ctx->kbuf + 2 * K, K, V, KP, cp.docterm, cp.iters,
                                                   cp.D, max_iter, heldout, ctx->partial);
@@ -668,7 +945,7 @@ int pylda_dirichlet_expectation(pylda_ctx* ctx, int K, int V, const double* eta_
 
 int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double* out) {
     if (!ctx) return 1;
-    if (which < 0 || which > 2 || n < 0 || (n > 0 && (!x || !out))) return fail(ctx, "pylda_special: bad arguments");
+    if (which < 0 || which > 4 || n < 0 || (n > 0 && (!x || !out))) return fail(ctx, "pylda_special: bad arguments");
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     double *dx = nullptr, *dy = nullptr;

@@ -1,0 +1,352 @@
+// Per-document VB E-step kernel, register-tile generation (sm_100a).
+//
+// Same mathematics as estep_kernel.cuh / estep_v2.cuh (reference variational_bayes.py:159-207
+// in product form).  The ncu captures of estep_v2 (profiles/r1b_*) showed the shared-memory pipe
+// at 50 % and the fp64 pipe at 35 % with two warps per scheduler: every trip re-read the whole
+// n_d x K tile from shared memory.  Here the tile is staged into shared memory ONCE by bulk-async
+// row copies (UBLKCP), moved ONCE into registers (a lane keeps R rows x 2J columns), and the
+// fixed-point trips run on registers only: per trip a lane issues 4*R*J DFMA, J LDS.128 for e and
+// J STS.128 for its column partial sums.  The R rows of a lane are independent dependency chains.
+// Shared memory keeps e (double buffered), the column partials and -- after the last trip --
+// the c*phi rows that leave by bulk reduce-add (UBLKRED), as before.
+//
+// A group of W warps owns one document of at most W * LN * R rows (LN = 32/LK row lanes);
+// longer documents use estep_v2 (shared-memory tile) or the streaming kernel.
+#pragma once
+#include "estep_v2.cuh"
+
+namespace pylda {
+
+// rows a lane keeps in registers: 4*J*R registers of tile
+template <int J>
+struct RtRows {
+    static constexpr int R = (J <= 5) ? 8 : (J <= 7) ? 6 : (J <= 8) ? 5 : (J <= 13) ? 3 : 2;
+};
+
+template <int LK, int J, int W>
+struct RtCfg {
+    static constexpr int LN = 32 / LK;
+    static constexpr int R = RtRows<J>::R;
+    static constexpr int KPAD = 2 * LK * J;
+    static constexpr int GT = 32 * W;
+    static constexpr int U = (KPAD + GT - 1) / GT;
+    // butterfly levels over the row lanes before the shared-memory reduce-scatter, so that an
+    // owner sums at most 16 partials
+    static constexpr int NB = (W * LN > 64) ? 3 : (W * LN > 32) ? 2 : (W * LN > 16) ? 1 : 0;
+    static constexpr int NP = (W * LN) >> NB;
+    static constexpr int CAP = W * LN * R;    // rows per document group
+};
+
+// Everything between "tile is in shared memory" and "phi rows are in shared memory" for a warp
+// that holds RU row groups (RU * LN rows) of the document in registers.
+template <int LK, int J, int W, int RU>
+__device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* spart, double* red, const double* cnt,
+                                        const double* mwr, double* tile, int n, int g, int gt, int gw, int lane,
+                                        bool warp_owns, const double (&alr)[RtCfg<LK, J, W>::U],
+                                        double (&gamr)[RtCfg<LK, J, W>::U], double (&er)[RtCfg<LK, J, W>::U],
+                                        double& lacc_out) {
+    using C = RtCfg<LK, J, W>;
+    constexpr int LN = C::LN, R = C::R, KPAD = C::KPAD, GT = C::GT, U = C::U, NB = C::NB, NP = C::NP;
+    constexpr int RA = RU > 0 ? RU : 1;
+    const int kl = lane % LK, nl = lane / LK;
+    const int K = p.K, ST = p.ST, KP2 = p.KP >> 1;
+    const int rbase = gw * LN * R + nl;          // lane's rows: rbase + i*LN
+
+    // ---- tile -> registers (once per document) ----------------------------------------------
+    double b[RA][2 * J];
+    double cw[RA];
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+        const int r = rbase + i * LN;
+        const double* rowp = tile + (size_t)(r < n ? r : 0) * ST + 2 * kl;   // rows >= n: a valid row with weight 0
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(rowp + 2 * LK * j);
+            b[i][2 * j] = v.x;
+            b[i][2 * j + 1] = v.y;
+        }
+        cw[i] = cnt[r];                          // staged as 0 for rows >= n
+    }
+
+    double w[RA], part[RA];
+    int it = 0;
+    const double tolK = p.tol * (double)K;
+    while (true) {
+        const double* es = es2 + (it & 1) * KPAD;
+        // norm_n = B[n,:] . e : 2 chains per row, RU rows
+        double a0[RA], a1[RA];
+#pragma unroll
+        for (int i = 0; i < RU; ++i) a0[i] = a1[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const double2 ev = *reinterpret_cast<const double2*>(es + 2 * (kl + LK * j));
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+                a0[i] = fma(b[i][2 * j], ev.x, a0[i]);
+                a1[i] = fma(b[i][2 * j + 1], ev.y, a1[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RU; ++i) part[i] = a0[i] + a1[i];
+#pragma unroll
+        for (int o = 1; o < LK; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < RU; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+        }
+#pragma unroll
+        for (int i = 0; i < RU; ++i) w[i] = cw[i] * rcp_nr(part[i]);
+        // column partial sums of this lane -> (butterfly over NB row-lane bits) -> shared memory
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+                s0 = fma(w[i], b[i][2 * j], s0);
+                s1 = fma(w[i], b[i][2 * j + 1], s1);
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 16 >> q);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16 >> q);
+            }
+            if (NB == 0 || nl < (LN >> NB))
+                *reinterpret_cast<double2*>(spart + (gw * (LN >> NB) + (NB == 0 ? nl : nl)) * KPAD + 2 * (kl + LK * j)) =
+                    make_double2(s0, s1);
+        }
+        gsync<W>(g);
+        // owners: gamma update (:185), |d gamma| (:187), speculative e for the next trip
+        double gn[U], en[U];
+        double dsum = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = gt + GT * u;
+            double ss0 = 0.0, ss1 = 0.0;
+            if (k < K) {
+#pragma unroll
+                for (int q = 0; q < NP; q += 2) {
+                    ss0 += spart[q * KPAD + k];
+                    if (q + 1 < NP) ss1 += spart[(q + 1) * KPAD + k];
+                }
+            }
+            gn[u] = fma(er[u], ss0 + ss1, alr[u]);
+            if (k < K) dsum += fabs(gn[u] - gamr[u]);
+        }
+        if (warp_owns) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) en[u] = exp_digamma(gn[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) en[u] = 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) gamr[u] = gn[u];                     // :188
+        ++it;
+        {
+            double* esn = es2 + (it & 1) * KPAD;                         // the buffer the NEXT trip reads
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = gt + GT * u;
+                if (k < K) esn[k] = en[u];
+            }
+        }
+        dsum = warp_sum(dsum);
+        if (W > 1) {
+            if (lane == 0) red[gw] = dsum;
+            gsync<W>(g);
+            dsum = 0.0;
+#pragma unroll
+            for (int x = 0; x < W; ++x) dsum += red[x];
+        } else {
+            __syncwarp();
+        }
+        if (dsum <= tolK || it >= p.max_iter) break;                     // :189-190 / :174
+#pragma unroll
+        for (int u = 0; u < U; ++u) er[u] = en[u];
+    }
+
+    // ---- phi from the LAST e (buffer (it-1)&1; w[] and part[] are those of the last trip) -------
+    const double* es = es2 + ((it - 1) & 1) * KPAD;
+    double lacc = 0.0;
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+        const int r = rbase + i * LN;
+        if (r < n && kl == 0) lacc = fma(cw[i], mwr[r] + log(part[i]), lacc);   // sum_n c_n logsumexp_n
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const double2 ev = *reinterpret_cast<const double2*>(es + 2 * (kl + LK * j));
+        if (kl + LK * j < KP2) {
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+                const int r = rbase + i * LN;
+                if (r < n)
+                    *reinterpret_cast<double2*>(tile + (size_t)r * ST + 2 * (kl + LK * j)) =
+                        make_double2(w[i] * b[i][2 * j] * ev.x, w[i] * b[i][2 * j + 1] * ev.y);   // c_n phi_nk (:207)
+            }
+        }
+    }
+    lacc_out = lacc;
+    return it;
+}
+
+template <int LK, int J, int W>
+__global__ void __launch_bounds__(256) estep_rt(const EParams p) {
+    using C = RtCfg<LK, J, W>;
+    constexpr int LN = C::LN, R = C::R, KPAD = C::KPAD, GT = C::GT, U = C::U, CAP = C::CAP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int g = tid / GT;
+    const int gt = tid - g * GT;
+    const int gw = gt >> 5;
+    const int lane = tid & 31;
+    const int K = p.K, KP = p.KP, ST = p.ST;
+
+    unsigned char* gs = smem_raw + (size_t)g * p.group_bytes;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(gs);
+    int* cur = reinterpret_cast<int*>(gs + 8);
+    double* es2 = reinterpret_cast<double*>(gs + 16);
+    double* spart = reinterpret_cast<double*>(gs + p.off_spart);
+    double* red = reinterpret_cast<double*>(gs + p.off_red);
+    double* cnt = reinterpret_cast<double*>(gs + p.off_cnt);
+    double* mwr = reinterpret_cast<double*>(gs + p.off_mwr);
+    int* rid = reinterpret_cast<int*>(gs + p.off_rid);
+    double* tile = reinterpret_cast<double*>(gs + p.off_tile);
+
+    for (int i = 16 + gt * 8; i < p.group_bytes; i += GT * 8) *reinterpret_cast<double*>(gs + i) = 0.0;
+    if (gt == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double alr[U], gamr[U], er[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int k = gt + GT * u;
+        alr[u] = (k < K) ? p.alpha[k] : 1.0;
+        gamr[u] = 1.0;
+        er[u] = 0.0;
+    }
+    const bool warp_owns = gw * 32 < K;
+    uint32_t parity = 0;
+    int nxt = 0;
+    if (gt == 0) nxt = atomicAdd(p.counter, 1);
+
+    while (true) {
+        bulk_wait_read0();
+        int idx;
+        if (W == 1) {
+            idx = __shfl_sync(0xffffffffu, nxt, 0);
+        } else {
+            if (gt == 0) *cur = nxt;
+            gsync<W>(g);
+            idx = *cur;
+        }
+        if (idx >= p.ndocs) break;
+        if (gt == 0) nxt = atomicAdd(p.counter, 1);
+        const int d = p.order[idx];
+        const long long base = p.row_ptr[d];
+        const int n = (int)(p.row_ptr[d + 1] - base);     // host guarantees n <= CAP for this class
+
+        if (gt == 0) mbar_expect_tx(mbar, (uint32_t)n * (uint32_t)KP * 8u);
+        int csum = 0;
+        for (int r = gt; r < CAP; r += GT) {
+            int c = 0;
+            if (r < n) {
+                const int id = p.ids[base + r];
+                c = p.cts[base + r];
+                rid[r] = id;
+                mwr[r] = p.mw[id];
+                bulk_g2s(tile + (size_t)r * ST, p.Bt + (size_t)id * KP, (uint32_t)KP * 8u, mbar);
+            }
+            cnt[r] = (double)c;
+            csum += c;
+        }
+        csum = __reduce_add_sync(0xffffffffu, csum);
+        double Nd = (double)csum;
+        if (W > 1) {
+            if (lane == 0) red[gw] = Nd;
+            gsync<W>(g);
+            Nd = 0.0;
+#pragma unroll
+            for (int x = 0; x < W; ++x) Nd += red[x];
+        }
+        const double g0 = Nd / (double)K;                  // gamma0 = alpha + N_d / K   (:165)
+#pragma unroll
+        for (int u = 0; u < U; ++u) gamr[u] = alr[u] + g0;
+        if (warp_owns) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) er[u] = exp_digamma(gamr[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = gt + GT * u;
+                if (k < K) es2[k] = er[u];
+            }
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        gsync<W>(g);
+
+        // rows of this warp: [gw*LN*R, gw*LN*R + RU*LN)
+        int RU = (n - gw * LN * R + LN - 1) / LN;
+        RU = RU < 0 ? 0 : (RU > R ? R : RU);
+        double lacc = 0.0;
+        int it = 0;
+#define PYLDA_RT_CASE(X)                                                                                     \
+    case X:                                                                                                  \
+        if constexpr (X <= R)                                                                                \
+            it = rt_trips<LK, J, W, X>(p, es2, spart, red, cnt, mwr, tile, n, g, gt, gw, lane, warp_owns, alr, \
+                                       gamr, er, lacc);                                                      \
+        break;
+        switch (RU) {
+            PYLDA_RT_CASE(0) PYLDA_RT_CASE(1) PYLDA_RT_CASE(2) PYLDA_RT_CASE(3) PYLDA_RT_CASE(4)
+            PYLDA_RT_CASE(5) PYLDA_RT_CASE(6) PYLDA_RT_CASE(7) PYLDA_RT_CASE(8)
+        }
+#undef PYLDA_RT_CASE
+        fence_async_smem();   // generic-proxy writes of phi -> visible to the bulk-async engine
+
+        // ---- per-document ELBO pieces and gamma write-back ------------------------------------
+        double t1 = lacc, sg = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = gt + GT * u;
+            if (k < K) {
+                const double gk = gamr[u];
+                const double ek = er[u];
+                const double dk = gk - alr[u];
+                t1 += lgamma(gk);                                            // :197
+                if (ek > 0.0 && dk != 0.0) t1 -= log(ek) * dk;               // - sum_k psi_k sum_n c_n phi_nk
+                sg += gk;
+                p.gamma[(size_t)d * K + k] = gk;                             // :212 / :216
+            }
+        }
+        t1 = warp_sum(t1);
+        sg = warp_sum(sg);
+        if (W > 1) {
+            if (lane == 0) {
+                red[W + 2 * gw] = t1;
+                red[W + 2 * gw + 1] = sg;
+            }
+        }
+        gsync<W>(g);   // all phi rows written (and red[] complete)
+        for (int r = gt; r < n; r += GT)
+            bulk_red_add_f64(p.phi_ss + (size_t)rid[r] * KP, tile + (size_t)r * ST, (uint32_t)KP * 8u);
+        bulk_commit();
+        if (gt == 0) {
+            if (W > 1) {
+                t1 = 0.0;
+                sg = 0.0;
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    t1 += red[W + 2 * x];
+                    sg += red[W + 2 * x + 1];
+                }
+            }
+            p.docterm[d] = t1 - lgamma(sg);                                  // - lgamma(sum_k gamma_k), :197
+            p.iters[d] = it;
+        }
+    }
+}
+
+}  // namespace pylda

@@ -229,7 +229,8 @@ __global__ void k_special(int which, long long n, const double* __restrict__ x, 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[i] = which == 0 ? digamma_pos(v) : which == 1 ? exp_digamma_shifted(v, 0.0) : lgamma(v);
+    out[i] = which == 0 ? digamma_pos(v) : which == 1 ? exp_digamma_shifted(v, 0.0) : which == 2 ? lgamma(v)
+           : which == 3 ? rcp_nr(v) : exp_digamma(v);
 }
 
 }  // namespace pylda

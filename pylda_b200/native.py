@@ -240,7 +240,7 @@ class EStepContext(object):
     def special(self, which, x):
         x = numpy.ascontiguousarray(x, dtype=numpy.float64).reshape(-1)
         out = numpy.empty_like(x)
-        code = {"digamma": 0, "exp_digamma": 1, "lgamma": 2}[which]
+        code = {"digamma": 0, "exp_digamma": 1, "lgamma": 2, "rcp": 3, "exp_digamma_v2": 4}[which]
         self._check(self._lib.pylda_special(self._h, code, x.shape[0], _dp(x), _dp(out)), "pylda_special")
         return out
 

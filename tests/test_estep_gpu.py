@@ -116,6 +116,14 @@ def test_special_functions_vs_scipy(ctx):
     erre = numpy.abs(ex[ok] - refe[ok]) / refe[ok] / numpy.maximum(1.0, numpy.abs(ref[ok]))
     print("exp(digamma) max err / cond", erre.max())
     assert erre.max() <= 1e-13
+    ex2 = ctx.special("exp_digamma_v2", x)
+    erre2 = numpy.abs(ex2[ok] - refe[ok]) / refe[ok] / numpy.maximum(1.0, numpy.abs(ref[ok]))
+    print("exp(digamma) v2 max err / cond", erre2.max())
+    assert erre2.max() <= 1e-13
+    rc = ctx.special("rcp", x)
+    errr = numpy.abs(rc * x - 1.0)
+    print("rcp max err", errr.max())
+    assert errr.max() <= 1e-15
     lg = ctx.special("lgamma", x)
     refl = sp.gammaln(x)
     errl = numpy.abs(lg - refl) / numpy.maximum(1.0, numpy.abs(refl))
