@@ -164,7 +164,7 @@ void free_model(pylda_ctx* c) {
 
 // (LK, J) lane shape for K topics: smallest padded width among the compiled shapes.
 // v2 adds (4, 13) (K = 100 -> 104 padded columns instead of 112); PYLDA_SHAPE="LK,J" forces a shape.
-bool pick_shape(int K, int* LK, int* J, bool v2 = false) {
+bool pick_shape(int K, int* LK, int* J, bool v2 = false, int W = 8) {
     const int pairs = (K + 1) / 2;
     if (v2) {
         const char* env = getenv("PYLDA_SHAPE");
@@ -184,7 +184,9 @@ bool pick_shape(int K, int* LK, int* J, bool v2 = false) {
             if (lk * j >= pairs && lk * j < best) { best = lk * j; *LK = lk; *J = j; found = true; }
         }
     }
-    if (v2 && 4 * 13 >= pairs && 4 * 13 < best) { best = 52; *LK = 4; *J = 13; found = true; }
+    // (4, 13): fewer shuffle levels and less padding, measured faster for groups of one or two warps
+    // (short documents); the wider (8, 7) keeps the per-lane register footprint of long rows smaller
+    if (v2 && W <= 2 && 4 * 13 >= pairs && 4 * 13 < best) { best = 52; *LK = 4; *J = 13; found = true; }
     if (!found && 32 * 16 >= pairs) { *LK = 32; *J = 16; found = true; }
     return found;
 }
@@ -201,14 +203,14 @@ const void* lookup_kernel(int LK, int J, bool res) {
     return nullptr;
 }
 
-const void* lookup_v2(int LK, int J, int W) {
+const void* lookup_v2(int LK, int J, int W, int V) {
     switch (LK) {
-        case 1: return estep_v2_lk1(J, W);
-        case 2: return estep_v2_lk2(J, W);
-        case 4: return estep_v2_lk4(J, W);
-        case 8: return estep_v2_lk8(J, W);
-        case 16: return estep_v2_lk16(J, W);
-        case 32: return estep_v2_lk32(J, W);
+        case 1: return estep_v2_lk1(J, W, V);
+        case 2: return estep_v2_lk2(J, W, V);
+        case 4: return estep_v2_lk4(J, W, V);
+        case 8: return estep_v2_lk8(J, W, V);
+        case 16: return estep_v2_lk16(J, W, V);
+        case 32: return estep_v2_lk32(J, W, V);
     }
     return nullptr;
 }
@@ -285,6 +287,24 @@ GroupLayout group_layout_rt(int W, int LK, int KPAD, int cap, int ST) {
     g.off_gam = 0;
     g.off_spart = o; o += NP * KPAD * 8;
     g.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    g.off_cnt = o;   o += cap * 8;
+    g.off_mwr = o;   o += cap * 8;
+    g.off_rid = o;   o += cap * 4;
+    o = align_up(o, 16);
+    g.off_tile = o;  o += cap * ST * 8 + KPAD * 8;
+    g.bytes = align_up(o, 128);
+    return g;
+}
+
+// shared-memory layout of one CTA of estep_cl (8 warps, `cap` rows of the document slice)
+GroupLayout group_layout_cl(int KPAD, int cap, int ST) {
+    GroupLayout g;
+    const int W = 8;
+    int o = 16;
+    o += KPAD * 8;                    // es
+    g.off_spart = o; o += W * KPAD * 8;
+    g.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    g.off_gam = o;   o += 2 * 8 * KPAD * 8;   // exchange slots [2][8][KPAD]
     g.off_cnt = o;   o += cap * 8;
     g.off_mwr = o;   o += cap * 8;
     g.off_rid = o;   o += cap * 4;
@@ -392,28 +412,33 @@ int launch_estep_v1(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_
     return 0;
 }
 
-// Length classes of the resident path: documents are sorted by n_d (descending) and each class
-// (W warps per document, at most G documents in flight per CTA) takes the documents whose tile
-// fits its per-group share of shared memory but not the next class's.  Default "8x1,4x2,2x4,1x8";
-// PYLDA_CLASSES overrides it for tuning (e.g. "8x1,4x2,2x4,2x8,1x8"), PYLDA_KERNEL=v1 selects the
-// first-generation kernel.
-struct ClassCfg { int W, G; };
+// Length classes of the single-CTA resident paths.  Documents are sorted by n_d (descending); every
+// class has a row capacity and a document goes to the class with the smallest capacity that holds it.
+//   "WxG"  estep_v2: tile in shared memory, W warps per document, G documents in flight per CTA
+//          (W*G <= 8: 8-warp CTAs; 8 < W*G <= 16: the 16-warp variant);
+//   "rW"   estep_rt: tile in registers, W warps per document, 8/W documents in flight per CTA.
+// PYLDA_CLASSES overrides the default list (tuning aid).
+struct ClassCfg { int kind, W, G; };
 
-std::vector<ClassCfg> class_config(int KPAD) {
+std::vector<ClassCfg> class_config() {
     std::vector<ClassCfg> out;
     const char* env = getenv("PYLDA_CLASSES");
-    std::string spec = env && *env ? env : "8x1,4x2,2x4,1x8";
+    std::string spec = env && *env ? env : "8x1,r8,r4,r2,r1";
     size_t pos = 0;
     while (pos < spec.size()) {
         size_t end = spec.find(',', pos);
         if (end == std::string::npos) end = spec.size();
+        const std::string item = spec.substr(pos, end - pos);
         int W = 0, G = 0;
-        if (sscanf(spec.substr(pos, end - pos).c_str(), "%dx%d", &W, &G) == 2 &&
-            (W == 1 || W == 2 || W == 4 || W == 8) && G >= 1 && W * G <= 8 && KPAD <= 128 * W)
-            out.push_back({W, G});
+        if (sscanf(item.c_str(), "r%d", &W) == 1) {
+            if (W == 1 || W == 2 || W == 4 || W == 8) out.push_back({1, W, 8 / W});
+        } else if (sscanf(item.c_str(), "%dx%d", &W, &G) == 2 &&
+                   (W == 1 || W == 2 || W == 4 || W == 8) && G >= 1 && W * G <= (W > 1 ? 16 : 8)) {
+            out.push_back({0, W, G});
+        }
         pos = end + 1;
     }
-    if (out.empty()) out = {{8, 1}};
+    if (out.empty()) out = {{0, 8, 1}};
     return out;
 }
 
@@ -478,9 +503,9 @@ int launch_streaming(pylda_ctx* ctx, Corpus& cp, long long nd, int LK, int J, in
 int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
     const int K = ctx->K, KP = ctx->KP;
     int LK = 0, J = 0, LK1 = 0, J1 = 0;
-    if (!pick_shape(K, &LK, &J, true) || !pick_shape(K, &LK1, &J1, false))
+    if (!pick_shape(K, &LK, &J, true, 8) || !pick_shape(K, &LK1, &J1, false))
         return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
-    const int KPAD = 2 * LK * J;
+    const int KPAD = 2 * LK * J;                           // shape of the long-document paths (cluster)
     const int LN = 32 / LK;
     const int ST = KP;                                     // rows packed (LDS.128 over LK lanes is conflict-free per quarter warp)
     const int smem_budget = (int)ctx->prop.sharedMemPerBlockOptin;
@@ -489,29 +514,30 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
 
     // Candidate classes, each with a row capacity; a document goes to the class with the smallest
     // capacity that holds it.  kind 0 = estep_v2 (tile in shared memory), kind 1 = estep_rt (tile
-    // in registers); documents above every capacity use the streaming kernel.
-    struct Cls { int kind, W, G, cap; const void* fn; long long lo, hi; };
+    // in registers); documents above every capacity use the cluster / streaming kernels.  The lane
+    // shape (LK, J) is chosen per class.
+    struct Cls { int kind, W, G, cap, LK, J; const void* fn; long long lo, hi; };
     std::vector<Cls> cls;
-    for (const ClassCfg& c : class_config(KPAD)) {
-        const int avail = (smem_budget / c.G) & ~127;
-        const GroupLayout g0 = group_layout_v2(c.W, LK, KPAD, 0, ST);
-        int n = (avail - g0.bytes - 128) / (ST * 8 + 20);
-        n = n / LN * LN;
-        const void* fn = lookup_v2(LK, J, c.W);
-        if (n > 0 && fn) cls.push_back({0, c.W, c.G, n, fn, 0, 0});
-    }
-    if (use_rt) {
-        for (int W = 8; W >= 1; W >>= 1) {
+    for (const ClassCfg& c : class_config()) {
+        int lk = 0, j = 0;
+        if (!pick_shape(K, &lk, &j, true, c.W)) continue;
+        const int kpad = 2 * lk * j, ln = 32 / lk;
+        if (kpad > 128 * c.W) continue;                    // at most 4 topics per owner thread
+        if (c.kind == 0) {
+            const int avail = (smem_budget / c.G) & ~127;
+            const GroupLayout g0 = group_layout_v2(c.W, lk, kpad, 0, ST);
+            int n = (avail - g0.bytes - 128) / (ST * 8 + 20);
+            n = n / ln * ln;
+            const void* fn = lookup_v2(lk, j, c.W, c.W * c.G > 8 ? 1 : 0);
+            if (n > 0 && fn) cls.push_back({0, c.W, c.G, n, lk, j, fn, 0, 0});
+        } else if (use_rt) {
             int R = 0;
-            const void* fn = lookup_rt(LK, J, W, &R);
+            const void* fn = lookup_rt(lk, j, c.W, &R);
             if (!fn) continue;
-            const int cap = W * LN * R;
-            const GroupLayout gl = group_layout_rt(W, LK, KPAD, cap, ST);
-            if ((8 / W) * gl.bytes > smem_budget) continue;
-            // drop v2 classes that the register-tile class makes redundant (not larger, not fewer warps per row)
-            cls.erase(std::remove_if(cls.begin(), cls.end(), [&](const Cls& c) { return c.kind == 0 && c.cap <= cap; }),
-                      cls.end());
-            cls.push_back({1, W, 8 / W, cap, fn, 0, 0});
+            const int cap = c.W * ln * R;
+            const GroupLayout gl = group_layout_rt(c.W, lk, kpad, cap, ST);
+            if (c.G * gl.bytes > smem_budget) continue;
+            cls.push_back({1, c.W, c.G, cap, lk, j, fn, 0, 0});
         }
     }
     std::sort(cls.begin(), cls.end(), [](const Cls& a, const Cls& b) { return a.cap > b.cap; });
@@ -528,10 +554,66 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     CK(cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(int), ctx->stream));
     for (int i = 0; i < NC; ++i) cls[i].lo = first_leq(cls[i].cap);
     for (int i = 0; i < NC; ++i) cls[i].hi = (i + 1 < NC) ? cls[i + 1].lo : D;
-    const long long nstream = NC ? cls[0].lo : D;
+    long long nlong = NC ? cls[0].lo : D;          // documents [0, nlong) fit no single-CTA class
+    ClassTimer timer;
+    long long nstream = nlong;
+    // The cluster path is correct (parity tests run it with PYLDA_KERNEL=cluster) but at 8 warps per SM
+    // its per-trip serial phase (cluster barrier + exp(psi) + reductions) still costs more than
+    // re-streaming from L2; it stays opt-in until that phase is shortened.
+    const void* fn_cl = (kv && !strcmp(kv, "cluster")) ? estep_cl_lookup(LK, J) : nullptr;
+    if (nlong > 0 && fn_cl) {
+        // cluster classes: C CTAs per document, each CTA keeps a slice of at most cap_cl rows resident
+        const GroupLayout g0 = group_layout_cl(KPAD, 0, ST);
+        int cap_cl = (smem_budget - g0.bytes - 128) / (ST * 8 + 20);
+        cap_cl = cap_cl / LN * LN;
+        if (cap_cl >= LN) {
+            const GroupLayout gl = group_layout_cl(KPAD, cap_cl, ST);
+            CK(cudaFuncSetAttribute(fn_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.bytes));
+            CK(cudaMemsetAsync(cp.docterm, 0, (size_t)std::max<long long>(D, 1) * sizeof(double), ctx->stream));
+            long long hi = nlong;                   // classes are carved from the short end of [0, nlong)
+            for (int C = 2; C <= 8 && hi > 0; C <<= 1) {
+                const long long lo = first_leq(C * cap_cl);      // documents [lo, hi) have n <= C * cap_cl
+                if (lo >= hi) continue;
+                const long long nd = hi - lo;
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.blockDim = dim3(256);
+                cfg.dynamicSmemBytes = (size_t)gl.bytes;
+                cfg.stream = ctx->stream;
+                cudaLaunchAttribute attr;
+                attr.id = cudaLaunchAttributeClusterDimension;
+                attr.val.clusterDim.x = C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+                cfg.attrs = &attr; cfg.numAttrs = 1;
+                cfg.gridDim = dim3((unsigned)(C * ctx->prop.multiProcessorCount));
+                int ncl = 0;
+                CK(cudaOccupancyMaxActiveClusters(&ncl, fn_cl, &cfg));
+                if (ncl < 1) break;                 // this cluster size cannot be scheduled: leave the rest to streaming
+                ncl = (int)std::min<long long>(ncl, nd);
+                cfg.gridDim = dim3((unsigned)(ncl * C));
+                EParams p;
+                memset(&p, 0, sizeof p);
+                p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+                p.order = cp.order + lo; p.ndocs = (int)nd; p.counter = nullptr;
+                p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
+                p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+                p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
+                p.W = 8; p.nmax = cap_cl; p.group_bytes = gl.bytes; p.off_groups = 0;
+                p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
+                p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
+                void* args[] = {&p};
+                timer.begin(ctx->stream, "cluster C=%d docs=%lld nmax=%d nmin=%d smem=%d clusters=%d", C, nd, ns[lo],
+                            ns[hi - 1], gl.bytes, ncl);
+                CK(cudaLaunchKernelExC(&cfg, fn_cl, args));
+                timer.end(ctx->stream);
+                st->n_launches++;
+                st->n_estep_launches++;
+                hi = lo;
+            }
+            nstream = hi;
+        }
+    }
     st->docs_streamed = nstream;
     st->docs_resident = D - nstream;
-    ClassTimer timer;
     if (nstream > 0) {
         timer.begin(ctx->stream, "streaming docs=%lld nmax=%d", nstream, ns[0]);
         if (launch_streaming(ctx, cp, nstream, LK1, J1, max_iter, tol, st, 0)) return 1;
@@ -542,18 +624,18 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         const long long nd = c.hi - c.lo;
         if (nd <= 0) continue;
         const int W = c.W;
+        const int kpad = 2 * c.LK * c.J, ln = 32 / c.LK;
         int nmax, G;
         GroupLayout gl;
         if (c.kind == 1) {
             nmax = c.cap;
-            gl = group_layout_rt(W, LK, KPAD, c.cap, ST);
-            G = 8 / W;
+            gl = group_layout_rt(W, c.LK, kpad, c.cap, ST);
+            G = c.G;
         } else {
-            nmax = std::max(LN, (ns[c.lo] + LN - 1) / LN * LN);
-            gl = group_layout_v2(W, LK, KPAD, nmax, ST);
+            nmax = std::max(ln, (ns[c.lo] + ln - 1) / ln * ln);
+            gl = group_layout_v2(W, c.LK, kpad, nmax, ST);
             // shorter documents than the class limit: pack more groups per CTA, up to the thread bound
-            G = std::min(8 / W, smem_budget / gl.bytes);
-            if (getenv("PYLDA_FIXED_G")) G = std::min(G, c.G);
+            G = std::min(c.G, smem_budget / gl.bytes);
         }
         if (G < 1) return fail(ctx, "internal: class %d needs %d B of shared memory per group", ci, gl.bytes);
         G = (int)std::min<long long>(G, nd);
@@ -576,8 +658,8 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
         p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
         void* args[] = {&p};
-        timer.begin(ctx->stream, "%s W=%d G=%d docs=%lld nmax=%d nmin=%d smem=%d grid=%lld", c.kind ? "rt" : "v2", W, G, nd,
-                    ns[c.lo], ns[c.hi - 1], smem, grid);
+        timer.begin(ctx->stream, "%s<%d,%d> W=%d G=%d docs=%lld nmax=%d nmin=%d smem=%d grid=%lld", c.kind ? "rt" : "v2",
+                    c.LK, c.J, W, G, nd, ns[c.lo], ns[c.hi - 1], smem, grid);
         CK(cudaLaunchKernel(c.fn, dim3((unsigned)grid), dim3(threads), args, (size_t)smem, ctx->stream));
         timer.end(ctx->stream);
         st->n_launches++;

@@ -1,0 +1,15 @@
+// Instantiations of the cluster (long-document) E-step kernel, one per lane shape.
+#include "estep_cl.cuh"
+#include "estep_dispatch.h"
+namespace pylda {
+const void* estep_cl_lookup(int LK, int J) {
+#define PYLDA_CASE(LL, JJ) if (LK == LL && J == JJ) return (const void*)estep_cl<LL, JJ>;
+#define PYLDA_ROW(LL) PYLDA_CASE(LL, 5) PYLDA_CASE(LL, 7) PYLDA_CASE(LL, 8)
+    PYLDA_ROW(1) PYLDA_ROW(2) PYLDA_ROW(4) PYLDA_ROW(8) PYLDA_ROW(16) PYLDA_ROW(32)
+    PYLDA_CASE(4, 13)
+    PYLDA_CASE(32, 16)
+#undef PYLDA_ROW
+#undef PYLDA_CASE
+    return nullptr;
+}
+}  // namespace pylda

@@ -7,13 +7,13 @@ const void* estep_kernel_lk4(int J, bool resident);
 const void* estep_kernel_lk8(int J, bool resident);
 const void* estep_kernel_lk16(int J, bool resident);
 const void* estep_kernel_lk32(int J, bool resident);
-// second generation (estep_v2.cuh): W = warps per document group (1, 2, 4, 8)
-const void* estep_v2_lk1(int J, int W);
-const void* estep_v2_lk2(int J, int W);
-const void* estep_v2_lk4(int J, int W);
-const void* estep_v2_lk8(int J, int W);
-const void* estep_v2_lk16(int J, int W);
-const void* estep_v2_lk32(int J, int W);
+// second generation (estep_v2.cuh): W = warps per document group (1, 2, 4, 8); V = 1: 16-warp CTAs
+const void* estep_v2_lk1(int J, int W, int V);
+const void* estep_v2_lk2(int J, int W, int V);
+const void* estep_v2_lk4(int J, int W, int V);
+const void* estep_v2_lk8(int J, int W, int V);
+const void* estep_v2_lk16(int J, int W, int V);
+const void* estep_v2_lk32(int J, int W, int V);
 // register-tile generation (estep_rt.cuh); *rows_per_lane = R, a group holds W * (32/LK) * R rows
 const void* estep_rt_lk1(int J, int W, int* rows_per_lane);
 const void* estep_rt_lk2(int J, int W, int* rows_per_lane);
@@ -21,4 +21,6 @@ const void* estep_rt_lk4(int J, int W, int* rows_per_lane);
 const void* estep_rt_lk8(int J, int W, int* rows_per_lane);
 const void* estep_rt_lk16(int J, int W, int* rows_per_lane);
 const void* estep_rt_lk32(int J, int W, int* rows_per_lane);
+// cluster generation (estep_cl.cuh): one long document per thread-block cluster of 2, 4 or 8 CTAs
+const void* estep_cl_lookup(int LK, int J);
 }  // namespace pylda

@@ -75,15 +75,19 @@ __device__ __forceinline__ void rows_accum(const double* rowp, size_t gstride, c
     }
 }
 
-template <int LK, int J, int W>
-__global__ void __launch_bounds__(256) estep_v2(const EParams p) {
+// V = 0: CTAs of up to 8 warps (255 registers available, two row groups in flight per lane);
+// V = 1: CTAs of up to 16 warps (128 registers, one row group per lane) -- more documents or more
+//        warps per document in flight per SM, to overlap one document's serial owner phase with
+//        another's row phase.
+template <int LK, int J, int W, int V>
+__global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) {
     constexpr int LN = 32 / LK;
     constexpr int KPAD = 2 * LK * J;
     constexpr int GT = 32 * W;
     constexpr int U = (KPAD + GT - 1) / GT;        // topics per owner thread
     constexpr bool BFLY = (W >= 4);                // reduce over the LN row-lanes by shuffles first
     constexpr int NP = BFLY ? W : W * LN;          // partial rows in spart
-    constexpr int RR = (2 * J <= 16) ? 2 : 1;      // row groups per trip-loop iteration (ILP vs registers)
+    constexpr int RR = (V == 0 && 2 * J <= 16) ? 2 : 1;   // row groups per trip-loop iteration (ILP vs registers)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;

@@ -12,7 +12,7 @@ cat gpurun_out/bench.json
 if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --docs ${NCU_DOCS:-200000} --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_bench.json 2> gpurun_out/ncu_launch.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:estep_kernel -c 5 -o gpurun_out/prof_estep -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:estep -c 6 -o gpurun_out/prof_estep -f \
     python bench.py --docs ${NCU_DOCS:-200000} --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_bench.json 2> gpurun_out/ncu_full.log
 fi
 tail -3 gpurun_out/pytest_gpu.log

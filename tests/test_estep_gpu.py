@@ -72,6 +72,52 @@ def test_against_oracle_shapes(ctx, K, V, D, length):
     print("stats", out["stats"])
 
 
+@pytest.mark.parametrize("kernel", ["v1", "v2", "cluster", "default"])
+def test_every_kernel_generation_matches_oracle(ctx, kernel, monkeypatch):
+    """The library holds four generations of the per-document kernel (first, shared-memory tile,
+    register tile [default], thread-block cluster for long documents); PYLDA_KERNEL selects one.
+    All of them must agree with the oracle on a corpus with short, medium and very long documents."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 100, 4000
+    a = synthetic.synthetic_corpus(120, V, seed=99, length="zipf")
+    b = synthetic.synthetic_corpus(6, V, seed=98, length="poisson", mean_len=5000)   # ~1000 unique terms each
+    row_ptr = numpy.concatenate([a[0], a[0][-1] + b[0][1:]])
+    ids, cts = numpy.concatenate([a[1], b[1]]), numpy.concatenate([a[2], b[2]])
+    assert numpy.diff(row_ptr).max() > 600          # long documents: cluster / streaming paths
+    eta = synthetic.initial_eta(K, V, seed=1)
+    alpha = numpy.full(K, 1.0 / K)
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6, return_iters=True)
+    if kernel != "default":
+        monkeypatch.setenv("PYLDA_KERNEL", kernel)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "kernel=%s" % kernel)
+    it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    assert numpy.array_equal(it, ref["iters"])
+    print("stats", out["stats"])
+
+
+def test_empty_and_single_term_documents(ctx):
+    """Ragged edge cases: documents with no terms (n_d = 0), one term, and a corpus of one document."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 12, 50
+    row_ptr = numpy.array([0, 0, 1, 1, 4, 4], dtype=numpy.int64)      # docs: empty, 1 term, empty, 3 terms, empty
+    ids = numpy.array([7, 3, 9, 49], dtype=numpy.int32)
+    cts = numpy.array([5, 1, 2, 1], dtype=numpy.int32)
+    eta = synthetic.initial_eta(K, V, seed=2)
+    alpha = numpy.linspace(0.05, 0.4, K)
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "ragged")
+    ctx.set_corpus(0, row_ptr[3:5] - 1, ids[1:], cts[1:])              # a single document
+    ref1 = O.e_step(row_ptr[3:5] - 1, ids[1:], cts[1:], eta, alpha, 50, 1e-6)
+    out1 = ctx.estep(0, eta, alpha, 50, 1e-6)
+    _check(out1, ref1["gamma"], ref1["phi_ss"], ref1["doc_ll"], "single")
+
+
 def test_warm_model_early_exit(ctx):
     """After a few EM iterations documents converge before the cap: trip counts must match the oracle's."""
     from oracle import estep_oracle as O
