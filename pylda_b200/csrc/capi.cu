@@ -280,7 +280,7 @@ GroupLayout group_layout_rt(int W, int LK, int KPAD, int cap, int ST) {
     GroupLayout g;
     const int LN = 32 / LK;
     const int WL = W * LN;
-    const int NB = WL > 64 ? 3 : WL > 32 ? 2 : WL > 16 ? 1 : 0;
+    const int NB = WL > 128 ? 3 : WL > 64 ? 2 : WL > 32 ? 1 : 0;
     const int NP = WL >> NB;
     int o = 16;                       // mbarrier + queue slot
     o += 2 * KPAD * 8;                // e, double buffered

@@ -31,8 +31,9 @@ struct RtCfg {
     static constexpr int GT = 32 * W;
     static constexpr int U = (KPAD + GT - 1) / GT;
     // butterfly levels over the row lanes before the shared-memory reduce-scatter, so that an
-    // owner sums at most 16 partials
-    static constexpr int NB = (W * LN > 64) ? 3 : (W * LN > 32) ? 2 : (W * LN > 16) ? 1 : 0;
+    // owner sums at most 32 partials (a butterfly level costs every lane 2J shuffle-adds; measured
+    // 25 % of the instructions of the W = 4 kernel when one level was used at 32 partials)
+    static constexpr int NB = (W * LN > 128) ? 3 : (W * LN > 64) ? 2 : (W * LN > 32) ? 1 : 0;
     static constexpr int NP = (W * LN) >> NB;
     static constexpr int CAP = W * LN * R;    // rows per document group
 };
@@ -95,23 +96,38 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
         }
 #pragma unroll
         for (int i = 0; i < RU; ++i) w[i] = cw[i] * rcp_nr(part[i]);
-        // column partial sums of this lane -> (butterfly over NB row-lane bits) -> shared memory
+        // column partial sums of this lane -> (butterfly over NB row-lane bits) -> shared memory.
+        // JB topic pairs at a time, rows in the outer loop: 2*JB independent accumulation chains.
+        constexpr int JB = 1;
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            double s0 = 0.0, s1 = 0.0;
+        for (int j0 = 0; j0 < J; j0 += JB) {
+            double s0[JB], s1[JB];
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) s0[jj] = s1[jj] = 0.0;
 #pragma unroll
             for (int i = 0; i < RU; ++i) {
-                s0 = fma(w[i], b[i][2 * j], s0);
-                s1 = fma(w[i], b[i][2 * j + 1], s1);
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    if (j0 + jj < J) {
+                        s0[jj] = fma(w[i], b[i][2 * (j0 + jj)], s0[jj]);
+                        s1[jj] = fma(w[i], b[i][2 * (j0 + jj) + 1], s1[jj]);
+                    }
+                }
             }
 #pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, 16 >> q);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, 16 >> q);
+            for (int jj = 0; jj < JB; ++jj) {
+                if (j0 + jj < J) {
+                    const int j = j0 + jj;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        s0[jj] += __shfl_xor_sync(0xffffffffu, s0[jj], 16 >> q);
+                        s1[jj] += __shfl_xor_sync(0xffffffffu, s1[jj], 16 >> q);
+                    }
+                    if (NB == 0 || nl < (LN >> NB))
+                        *reinterpret_cast<double2*>(spart + (gw * (LN >> NB) + nl) * KPAD + 2 * (kl + LK * j)) =
+                            make_double2(s0[jj], s1[jj]);
+                }
             }
-            if (NB == 0 || nl < (LN >> NB))
-                *reinterpret_cast<double2*>(spart + (gw * (LN >> NB) + (NB == 0 ? nl : nl)) * KPAD + 2 * (kl + LK * j)) =
-                    make_double2(s0, s1);
         }
         gsync<W>(g);
         // owners: gamma update (:185), |d gamma| (:187), speculative e for the next trip
@@ -120,20 +136,22 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int k = gt + GT * u;
-            double ss0 = 0.0, ss1 = 0.0;
+            double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
             if (k < K) {
 #pragma unroll
-                for (int q = 0; q < NP; q += 2) {
+                for (int q = 0; q < NP; q += 4) {
                     ss0 += spart[q * KPAD + k];
                     if (q + 1 < NP) ss1 += spart[(q + 1) * KPAD + k];
+                    if (q + 2 < NP) ss2 += spart[(q + 2) * KPAD + k];
+                    if (q + 3 < NP) ss3 += spart[(q + 3) * KPAD + k];
                 }
             }
-            gn[u] = fma(er[u], ss0 + ss1, alr[u]);
+            gn[u] = fma(er[u], (ss0 + ss1) + (ss2 + ss3), alr[u]);
             if (k < K) dsum += fabs(gn[u] - gamr[u]);
         }
         if (warp_owns) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) en[u] = exp_digamma(gn[u]);
+            for (int u = 0; u < U; ++u) en[u] = (W == 1) ? exp_digamma(gn[u]) : exp_digamma_imm(gn[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) en[u] = 0.0;
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
         for (int u = 0; u < U; ++u) gamr[u] = alr[u] + g0;
         if (warp_owns) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) er[u] = exp_digamma(gamr[u]);
+            for (int u = 0; u < U; ++u) er[u] = (W == 1) ? exp_digamma(gamr[u]) : exp_digamma_imm(gamr[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = gt + GT * u;

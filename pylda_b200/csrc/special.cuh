@@ -82,9 +82,60 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return r;
 }
 
-// exp(psi(x)) for x > 0 (x >= 1e-300): same construction as exp_digamma_shifted with c = 0 and
-// the Newton reciprocal.  Underflows to 0 exactly where exp(psi(x)) does (x <~ 1.4e-3).
+// Polynomial coefficients live in constant memory so that every Horner step is ONE DFMA with a
+// constant-bank operand (as immediates each 64-bit coefficient costs two extra IMAD.MOV; measured:
+// 18 % of all instructions of the register-tile kernel, profiles/r1b_estep_rt_W1_by_line.txt).
+// Generated / checked by tools/fit_special.py.
+//   c_exp: exp(r) on |r| <= ln2/2, degree 11, max relative error 1.7e-17
+//   c_g  : exp(psi(y)) = z + g(u)/z, u = 1/z^2, z = y - 1/2 >= 3.5, highest degree first
+__constant__ double c_exp[12] = {0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000011p-1, 0x1.555555555555ap-3,
+                                 0x1.555555554f0cfp-5, 0x1.111111110f225p-7, 0x1.6c16c187fbe02p-10, 0x1.a01a01b14378fp-13,
+                                 0x1.a01991ac8730ap-16, 0x1.71ddf5749d126p-19, 0x1.28b4057f44145p-22, 0x1.af631d0059becp-26};
+__constant__ double c_g[9] = {0x1.72c2625e26025p-2, -0x1.ab037fd41fbcdp-3, 0x1.16a7995f48852p-4, -0x1.4a0ddd7f70d64p-6,
+                              0x1.e1ae396a755f1p-8, -0x1.0315dff6af42ap-8, 0x1.d1a17ce364565p-9, -0x1.a4fa4f9f36231p-8,
+                              0x1.55555555553dap-5};
+
+// exp(y) for y <= 0, branch-free: y = n ln2 + r, degree-11 polynomial, exponent patched in.
+// Results below 2^-1020 are flushed to 0 (the reference's exp() would return a denormal there;
+// such e_k are 300 orders of magnitude below anything that reaches gamma, phi or the ELBO).
+__device__ __forceinline__ double exp_nonpos(double y) {
+    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52: n lands in the low word of t
+    const double t = fma(y, 0x1.71547652b82fep+0, SHIFT);
+    const double n = t - SHIFT;
+    double r = fma(n, -0x1.62e42fefa39efp-1, y);
+    r = fma(n, -0x1.abc9e3b39803fp-56, r);
+    double p = c_exp[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp[i]);
+    const int ni = __double2loint(t);
+    const double res = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    return y < -707.0 ? 0.0 : res;
+}
+
+// exp(psi(x)) for x > 0 (x >= 1e-300): same construction as exp_digamma_shifted with c = 0, the
+// Newton reciprocal and the branch-free exp.  Underflows to 0 where exp(psi(x)) < 1e-307 (x <~ 1.4e-3).
 __device__ __forceinline__ double exp_digamma(double x) {
+    const double x1 = x + 1.0, x2 = x + 2.0, x3 = x + 3.0;
+    const double a = x * x1, da = x + x1;
+    const double b = x2 * x3, db = x2 + x3;
+    const double P = a * b;
+    const double Q = fma(da, b, a * db);
+    const double z = x + 3.5;
+    const double r = rcp_nr(P * z);
+    const double invz = r * P;
+    const double qp = Q * (r * z);
+    const double u = invz * invz;
+    double g = c_g[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) g = fma(g, u, c_g[i]);
+    const double G = fma(invz, g, z);
+    return G * exp_nonpos(-qp);
+}
+
+// Same function with the coefficients as instruction immediates and the library exp(): more
+// instructions, but no uniform-register traffic -- measured faster in the register-starved
+// multi-warp register-tile kernels (estep_rt, W >= 2), slower everywhere else.
+__device__ __forceinline__ double exp_digamma_imm(double x) {
     const double x1 = x + 1.0, x2 = x + 2.0, x3 = x + 3.0;
     const double a = x * x1, da = x + x1;
     const double b = x2 * x3, db = x2 + x3;

@@ -45,7 +45,7 @@ class Inferencer(object):
     def parse_vocabulary(self, vocab):
         # inferencer.py:60-67 (ids in set() order; run with PYTHONHASHSEED=0 for reproducible ids)
         self._type_to_index, self._index_to_type = parse_vocabulary(vocab)
-        self._vocab = self._type_to_index.keys()
+        self._vocab = list(self._type_to_index.keys())    # a list, as under Python 2 (keeps the object picklable)
 
     def parse_data(self):
         raise NotImplementedError

@@ -1,0 +1,76 @@
+"""Multi-GPU path: one process per GPU, documents sharded by nnz, ONE NCCL all-reduce of the K x V
+statistics (+ ELBO scalars, alpha statistics) per E-step inside the library.  Needs >= 2 GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`); skipped on a single-GPU box."""
+import os
+import subprocess
+import tempfile
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for line in out.split("\n") if line.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+def _rank_main(rank, world, tmp):
+    import time
+    from pylda_b200 import native, synthetic
+    K, V = 100, 3000
+    row_ptr, ids, cts = synthetic.synthetic_corpus(400, V, seed=31, length="zipf")
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    ctx = native.EStepContext(rank)
+    id_path = os.path.join(tmp, "nccl_id")
+    if rank == 0:
+        uid = native.EStepContext.comm_unique_id()
+        with open(id_path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.replace(id_path + ".tmp", id_path)
+    else:
+        while not os.path.exists(id_path):
+            time.sleep(0.05)
+        uid = open(id_path, "rb").read()
+    ctx.comm_init(world, rank, uid)
+    b = native.shard_bounds(row_ptr, world)
+    ctx.set_corpus(0, *native.shard_csr(row_ptr, ids, cts, int(b[rank]), int(b[rank + 1])))
+    out = ctx.estep(0, eta, alpha, 50, 1e-6, want_alpha_ss=True)
+    numpy.savez(os.path.join(tmp, "rank%d.npz" % rank), gamma=out["gamma"], phi_ss=out["phi_ss"],
+                alpha_ss=out["alpha_ss"], doc_ll=out["doc_ll"], lo=b[rank], hi=b[rank + 1])
+    ctx.close()
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs at least 2 GPUs")
+def test_two_gpus_equal_one_gpu_and_oracle():
+    import torch.multiprocessing as mp
+    from oracle import estep_oracle as O
+    from pylda_b200 import native, synthetic
+    world = 2
+    K, V = 100, 3000
+    row_ptr, ids, cts = synthetic.synthetic_corpus(400, V, seed=31, length="zipf")
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_rank_main, args=(world, tmp), nprocs=world, join=True)
+        parts = [numpy.load(os.path.join(tmp, "rank%d.npz" % r)) for r in range(world)]
+        parts = [{k: p[k] for k in p.files} for p in parts]
+    single = native.EStepContext(0)
+    single.set_corpus(0, row_ptr, ids, cts)
+    one = single.estep(0, eta, alpha, 50, 1e-6, want_alpha_ss=True)
+    single.close()
+    gamma = numpy.concatenate([p["gamma"] for p in parts])
+    # every rank holds the all-reduced statistics
+    for p in parts:
+        assert numpy.allclose(p["phi_ss"], one["phi_ss"], rtol=1e-11, atol=1e-290)
+        assert numpy.allclose(p["alpha_ss"], one["alpha_ss"], rtol=1e-11)
+        assert abs(float(p["doc_ll"]) - one["doc_ll"]) <= 1e-11 * abs(one["doc_ll"])
+    assert numpy.array_equal(gamma, one["gamma"])            # per-document results do not depend on the shard
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6)
+    assert numpy.max(numpy.abs(gamma - ref["gamma"]) / ref["gamma"]) <= 1e-5
+    assert abs(one["doc_ll"] - ref["doc_ll"]) <= 1e-5 * abs(ref["doc_ll"])
