@@ -112,6 +112,17 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(D):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the per-document kernels of one E-step, from the
+    committed ncu --set full capture of this very workload (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_estep"]) if int(t["docs"]) == int(D) else None
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -282,7 +293,8 @@ def run_product(args):
         docs_total = allsum(float(D))
         res = ctx.get_results(0, gamma=False, phi=False)
         results[state] = dict(dev_ms=dev_ms, wall_ms=wall_ms, ker_ms=ker_ms, docs_total=docs_total, stats=st,
-                              doc_ll=res["doc_ll"], mean_trips=st["inner_iters"] / float(D))
+                              doc_ll=res["doc_ll"], mean_trips=st["inner_iters"] / docs_total,
+                              at_cap=st["docs_at_cap"])
 
     # ---- e2e: the reference-facing call with host buffers (pinned), at the headline state ----
     if args.state == "warm":
@@ -321,6 +333,13 @@ def run_product(args):
     achieved = algo / (head["ker_ms"] * 1e-3) / 1e9
     achieved_read = st["algo_read_bytes"] / (head["ker_ms"] * 1e-3) / 1e9
 
+    # secondary roofline: the fp64 pipe.  Algorithmic flops = 4*K per (row, trip) for the two mat-vecs
+    # (exp(psi), reciprocals and reductions not counted); peak = DFMA rate measured on this part by
+    # scripts/ubench/fp64_lat.cu (58.8 lanes/clk/SM * 148 SMs * 1.965 GHz * 2 flop = 34.2 TFLOP/s)
+    fp64_peak = 58.8 * 148 * 1.965e9 * 2 / 1e12
+    fp64_flops = 4.0 * K * st["row_trips"] / max(1, world)      # row_trips is summed over ranks
+    fp64_ach = fp64_flops / (head["ker_ms"] * 1e-3) / 1e12
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_single_core(row_ptr, ids, cts, eta_host, alpha, args.cpu_docs)
@@ -337,7 +356,7 @@ def run_product(args):
                     D, V, K, nnz),
                 "state": args.state + (" (eta0 ~ Gamma(100,0.01), EM iteration 1)" if args.state == "cold"
                                        else " (after 2 EM iterations)"),
-                "mean_inner_trips": head["mean_trips"], "docs_at_cap": st["docs_at_cap"],
+                "mean_inner_trips": head["mean_trips"], "docs_at_cap": head["at_cap"],
                 "local_parameter_iteration": 50, "converge_threshold": 1e-6,
                 "l2": "inputs larger than L2 (CSR + gamma + tables = %.1f GB per GPU)" % (
                     (12.0 * nnz + 8.0 * D * (K + 2) + 4 * 8.0 * V * K) / 1e9),
@@ -347,10 +366,17 @@ def run_product(args):
             "wall_ms_per_step": head["wall_ms"],
             "elbo_doc_ll": head["doc_ll"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "estep_kernel (all length classes)",
+                         "traffic": measured_traffic(D), "peak_source": peak_src,
+                         "kernel": "per-document E-step kernels of one E-step (estep_rt / estep_v2 / streaming, "
+                                   "one launch per length class)",
                          "kernel_ms": head["ker_ms"], "achieved_read": achieved_read,
                          "frac_read": achieved_read / peak,
-                         "note": "fixed-point trips are fp64-FMA/exp bound at %.1f trips/doc; see DESIGN.md" % head["mean_trips"]},
+                         "note": "binding roof at %.1f trips/doc is the fp64 pipe, not HBM (DESIGN.md 4.1); "
+                                 "see roofline_fp64" % head["mean_trips"]},
+            "roofline_fp64": {"bound": "fp64 pipe", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": fp64_ach / fp64_peak,
+                              "flops": "4*K per (term row, trip) of the two mat-vecs; exp(psi) and reductions not counted",
+                              "peak_source": "measured DFMA rate, scripts/ubench/fp64_lat.cu (profiles/r1_fp64_ubench.txt)"},
             other: {"value": o["docs_total"] / (o["dev_ms"] * 1e-3), "ms_per_step": o["dev_ms"], "kernel_ms": o["ker_ms"],
                     "mean_inner_trips": o["mean_trips"], "elbo_doc_ll": o["doc_ll"],
                     "roofline_frac": o["stats"]["algo_total_bytes"] / (o["ker_ms"] * 1e-3) / 1e9 / peak,

@@ -31,12 +31,13 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 1
+#define PYLDA_ABI_VERSION 2
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
 
-/* Filled by the E-step entry points (all ranks fill their LOCAL values). */
+/* Filled by the E-step entry points.  n_docs, nnz, times, bytes and launch counts are LOCAL to the
+ * rank; inner_iters, docs_at_cap and row_trips are summed over ranks once pylda_comm_init was called. */
 typedef struct pylda_stats {
     int64_t n_docs;            /* documents processed by this context (local shard)          */
     int64_t nnz;               /* (doc, term) pairs processed                                 */
@@ -52,6 +53,7 @@ typedef struct pylda_stats {
     int32_t n_estep_launches;  /* of which per-document E-step kernels                        */
     int64_t docs_resident;     /* documents whose tile was staged in shared memory            */
     int64_t docs_streamed;     /* documents whose tile was re-streamed from L2/HBM            */
+    double  row_trips;         /* sum_d n_d * iters_d: 4*KP*row_trips = fp64 flops of the mat-vecs */
 } pylda_stats;
 
 /* ABI version of the loaded library (== PYLDA_ABI_VERSION of the header it was built from). */

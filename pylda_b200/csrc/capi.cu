@@ -500,6 +500,46 @@ int launch_streaming(pylda_ctx* ctx, Corpus& cp, long long nd, int LK, int J, in
     return 0;
 }
 
+// second-generation streaming kernel for documents [lo, hi) of the sorted order (all with n <= nmax)
+int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int nmax, int LK, int J, int max_iter,
+                   double tol, pylda_stats* st, int counter_slot, int* launched) {
+    *launched = 0;
+    const void* fn = estep_stream_lookup(LK, J);
+    if (!fn) return 0;
+    const int K = ctx->K, KP = ctx->KP;
+    const int KPAD = 2 * LK * J, LN = 32 / LK, W = 8;
+    const int cap = (nmax + LN - 1) / LN * LN;
+    GroupLayout gl;
+    int o = 16 + KPAD * 8;
+    gl.off_spart = o; o += W * KPAD * 8;
+    gl.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    gl.off_cnt = o;   o += cap * 8;
+    gl.off_rid = o;   o += cap * 4;
+    gl.bytes = align_up(o, 128);
+    if (gl.bytes > (int)ctx->prop.sharedMemPerBlockOptin / 2) return 0;      // keep two CTAs per SM
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, gl.bytes, 0));
+    if (occ < 1) return 0;
+    const long long nd = hi - lo;
+    const long long grid = std::min<long long>((long long)ctx->prop.multiProcessorCount * occ, nd);
+    EParams p;
+    memset(&p, 0, sizeof p);
+    p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+    p.order = cp.order + lo; p.ndocs = (int)nd; p.counter = ctx->counters + counter_slot;
+    p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
+    p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+    p.K = K; p.KP = KP; p.ST = KP; p.max_iter = max_iter; p.tol = tol;
+    p.W = W; p.nmax = cap; p.group_bytes = gl.bytes;
+    p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt; p.off_rid = gl.off_rid;
+    void* args[] = {&p};
+    CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)gl.bytes, ctx->stream));
+    st->n_launches++;
+    st->n_estep_launches++;
+    *launched = 1;
+    return 0;
+}
+
 int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
     const int K = ctx->K, KP = ctx->KP;
     int LK = 0, J = 0, LK1 = 0, J1 = 0;
@@ -544,7 +584,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     // equal capacities: keep the first
     cls.erase(std::unique(cls.begin(), cls.end(), [](const Cls& a, const Cls& b) { return a.cap == b.cap; }), cls.end());
     const int NC = (int)cls.size();
-    if (NC + 1 > 16) return fail(ctx, "too many length classes");
+    if (NC > 13) return fail(ctx, "too many length classes");
 
     const std::vector<int>& ns = cp.n_sorted;
     const long long D = cp.D;
@@ -615,9 +655,25 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     st->docs_streamed = nstream;
     st->docs_resident = D - nstream;
     if (nstream > 0) {
-        timer.begin(ctx->stream, "streaming docs=%lld nmax=%d", nstream, ns[0]);
-        if (launch_streaming(ctx, cp, nstream, LK1, J1, max_iter, tol, st, 0)) return 1;
-        timer.end(ctx->stream);
+        // second-generation streaming kernel for everything whose ids/counts fit its shared memory
+        // (n up to ~9000 terms); the first-generation one remains for pathologically long documents
+        long long s2_lo = nstream;
+        if (!(kv && !strcmp(kv, "stream1"))) {
+            const int limit = ((int)ctx->prop.sharedMemPerBlockOptin / 2 - 16 - 2 * LK * J * 8 * 9 - 512) / 12;
+            s2_lo = first_leq(limit);
+            if (s2_lo < nstream) {
+                int launched = 0;
+                timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream - s2_lo, ns[s2_lo]);
+                if (launch_stream2(ctx, cp, s2_lo, nstream, ns[s2_lo], LK, J, max_iter, tol, st, 15, &launched)) return 1;
+                timer.end(ctx->stream);
+                if (!launched) s2_lo = nstream;
+            }
+        }
+        if (s2_lo > 0) {
+            timer.begin(ctx->stream, "streaming docs=%lld nmax=%d", s2_lo, ns[0]);
+            if (launch_streaming(ctx, cp, s2_lo, LK1, J1, max_iter, tol, st, 0)) return 1;
+            timer.end(ctx->stream);
+        }
     }
     for (int ci = 0; ci < NC; ++ci) {
         const Cls& c = cls[ci];
@@ -835,7 +891,8 @@ int pylda_set_model(pylda_ctx* ctx, int K, int V, const double* eta_KxV, const d
         CK(dalloc(&ctx->eta, kv));
         CK(dalloc(&ctx->alpha, (size_t)K));
         CK(dalloc(&ctx->Elt, vkp));
-        CK(dalloc(&ctx->Bt, vkp));
+        CK(dalloc(&ctx->Bt, vkp + 1024));     // + slack: unpredicated over-read past the last word's row
+        CK(cudaMemsetAsync(ctx->Bt + vkp, 0, 1024 * sizeof(double), ctx->stream));
         CK(dalloc(&ctx->mw, (size_t)V));
         CK(dalloc(&ctx->phi, vkp));
         CK(dalloc(&ctx->phi_KV, kv));
@@ -888,7 +945,7 @@ int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     k_reduce_terms<<<nred, 256, 0, ctx->stream>>>(ctx->phi, ctx->Elt, ctx->kbuf + 2 * K, K, V, KP, cp.docterm, cp.iters,
-                                                  cp.D, max_iter, heldout, ctx->partial);
+                                                  cp.row_ptr, cp.D, max_iter, heldout, ctx->partial);
     k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->partial, nred, NTERMS, ctx->scal);
     st.n_launches += 2;
     ctx->have_alpha_ss = false;
@@ -905,7 +962,7 @@ int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int
     if (ctx->comm) {
         // [scal5] = local D so that doc_ll can add D_total * alpha_term
         const double dloc = (double)cp.D;
-        CK(cudaMemcpyAsync(ctx->scal + 5, &dloc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->scal + 7, &dloc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         int rc = g_nccl.GroupStart();
         if (!rc) rc = g_nccl.AllReduce(ctx->phi, ctx->phi, (size_t)V * KP, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
         if (!rc) rc = g_nccl.AllReduce(ctx->scal, ctx->scal, 8, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
@@ -918,7 +975,7 @@ int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaMemcpyAsync(ctx->last_scal, ctx->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->comm) ctx->last_scal[5] = (double)cp.D;
+    if (!ctx->comm) ctx->last_scal[7] = (double)cp.D;
     cp.has_results = true;
     cp.results_K = K;
     float ms = 0;
@@ -930,6 +987,7 @@ int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int
     st.nnz = cp.nnz;
     st.inner_iters = (int64_t)llround(ctx->last_scal[3]);
     st.docs_at_cap = (int64_t)llround(ctx->last_scal[4]);
+    st.row_trips = ctx->last_scal[5];
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;
     st.algo_total_bytes = st.algo_read_bytes + 8.0 * (double)cp.D * K + 8.0 * (double)cp.nnz * K;
     if (stats) *stats = st;
@@ -962,7 +1020,7 @@ int pylda_get_results(pylda_ctx* ctx, int slot, double* gamma_DxK, double* phi_s
     if (iters_D && cp.D) CK(cudaMemcpyAsync(iters_D, cp.iters, (size_t)cp.D * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const double* s = ctx->last_scal;
-    if (doc_ll) *doc_ll = s[5] * ctx->alpha_term + s[0] - s[1];     // variational_bayes.py:195-199
+    if (doc_ll) *doc_ll = s[7] * ctx->alpha_term + s[0] - s[1];     // variational_bayes.py:195-199
     if (words_ll) *words_ll = s[2];                                  // :204
     return 0;
 }

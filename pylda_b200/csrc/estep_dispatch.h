@@ -23,4 +23,6 @@ const void* estep_rt_lk16(int J, int W, int* rows_per_lane);
 const void* estep_rt_lk32(int J, int W, int* rows_per_lane);
 // cluster generation (estep_cl.cuh): one long document per thread-block cluster of 2, 4 or 8 CTAs
 const void* estep_cl_lookup(int LK, int J);
+// second-generation streaming kernel (documents longer than every resident class)
+const void* estep_stream_lookup(int LK, int J);
 }  // namespace pylda

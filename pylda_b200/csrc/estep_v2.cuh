@@ -359,3 +359,244 @@ __global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) 
 }
 
 }  // namespace pylda
+
+namespace pylda {
+
+// ---- streaming variant: documents too long for any resident class -----------------------------
+// One CTA of 8 warps per document, two CTAs per SM.  The B rows are NOT staged: every trip re-reads
+// them from L2 (the V x KP table is 80 MB at the headline config, L2 is 126 MB) with unpredicated
+// LDG.128, two row groups in flight per lane; only term ids and counts live in shared memory.
+// Same trip structure as estep_v2 with W = 8; phi leaves by red.global.add.f64.
+template <int LK, int J, int RR>
+__device__ __forceinline__ void rows_accum_global(const double* __restrict__ Bt, int KP, int kl, const int* ridp,
+                                                  const double* cntp, int gstride_rows, const double (&e)[2 * J],
+                                                  double (&s)[2 * J]) {
+    double b[RR][2 * J];
+    double part[RR];
+#pragma unroll
+    for (int i = 0; i < RR; ++i) {
+        const double* rowp = Bt + (size_t)ridp[i * gstride_rows] * KP + 2 * kl;
+        part[i] = row_dot<LK, J>(rowp, e, b[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < RR; ++i) {
+        const double w = cntp[i * gstride_rows] * rcp_nr(part[i]);
+#pragma unroll
+        for (int c = 0; c < 2 * J; ++c) s[c] = fma(w, b[i][c], s[c]);
+    }
+}
+
+template <int LK, int J>
+__global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
+    constexpr int W = 8;
+    constexpr int LN = 32 / LK;
+    constexpr int KPAD = 2 * LK * J;
+    constexpr int GT = 256;
+    constexpr int U = (KPAD + GT - 1) / GT;
+    constexpr int RR = (2 * J <= 16) ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int gt = threadIdx.x;
+    const int gw = gt >> 5;
+    const int lane = gt & 31;
+    const int kl = lane % LK;
+    const int nl = lane / LK;
+    const int K = p.K, KP = p.KP;
+    const int KP2 = KP >> 1;
+
+    unsigned char* gs = smem_raw;
+    int* cur = reinterpret_cast<int*>(gs + 8);
+    double* es = reinterpret_cast<double*>(gs + 16);
+    double* spart = reinterpret_cast<double*>(gs + p.off_spart);     // [W][KPAD]
+    double* red = reinterpret_cast<double*>(gs + p.off_red);
+    double* cnt = reinterpret_cast<double*>(gs + p.off_cnt);
+    int* rid = reinterpret_cast<int*>(gs + p.off_rid);
+
+    for (int i = 16 + gt * 8; i < p.group_bytes; i += GT * 8) *reinterpret_cast<double*>(gs + i) = 0.0;
+    __syncthreads();
+
+    double alr[U], gamr[U], er[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int k = gt + GT * u;
+        alr[u] = (k < K) ? p.alpha[k] : 1.0;
+        gamr[u] = 1.0;
+        er[u] = 0.0;
+    }
+    const bool warp_owns = gw * 32 < K;
+    int nxt = 0;
+    if (gt == 0) nxt = atomicAdd(p.counter, 1);
+
+    while (true) {
+        if (gt == 0) *cur = nxt;
+        __syncthreads();
+        const int idx = *cur;
+        if (idx >= p.ndocs) break;
+        if (gt == 0) nxt = atomicAdd(p.counter, 1);
+        const int d = p.order[idx];
+        const long long base = p.row_ptr[d];
+        const int n = (int)(p.row_ptr[d + 1] - base);       // host guarantees n <= p.nmax
+        const int npad = (n + LN - 1) / LN * LN;
+        const int NG = npad / LN;
+        int csum = 0;
+        for (int r = gt; r < npad; r += GT) {
+            const bool real = r < n;
+            rid[r] = p.ids[base + (real ? r : 0)];          // pad rows: a valid row with weight 0
+            const int c = real ? p.cts[base + r] : 0;
+            cnt[r] = (double)c;
+            csum += c;
+        }
+        csum = __reduce_add_sync(0xffffffffu, csum);
+        if (lane == 0) red[gw] = (double)csum;
+        __syncthreads();
+        double Nd = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) Nd += red[w];
+        const double g0 = Nd / (double)K;                   // gamma0 = alpha + N_d / K   (:165)
+#pragma unroll
+        for (int u = 0; u < U; ++u) gamr[u] = alr[u] + g0;
+        if (warp_owns) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) er[u] = exp_digamma(gamr[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = gt + GT * u;
+                if (k < K) es[k] = er[u];
+            }
+        }
+        __syncthreads();
+
+        double e[2 * J];
+        int it = 0;
+        const double tolK = p.tol * (double)K;
+        while (true) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(es + 2 * (kl + LK * j));
+                e[2 * j] = v.x;
+                e[2 * j + 1] = v.y;
+            }
+            double s[2 * J];
+#pragma unroll
+            for (int i = 0; i < 2 * J; ++i) s[i] = 0.0;
+            {
+                const int* ridp = rid + gw * LN + nl;
+                const double* cntp = cnt + gw * LN + nl;
+                int q = gw;
+                for (; q + W * (RR - 1) < NG; q += W * RR, ridp += RR * W * LN, cntp += RR * W * LN)
+                    rows_accum_global<LK, J, RR>(p.Bt, KP, kl, ridp, cntp, W * LN, e, s);
+                if (RR > 1) {
+                    for (; q < NG; q += W, ridp += W * LN, cntp += W * LN)
+                        rows_accum_global<LK, J, 1>(p.Bt, KP, kl, ridp, cntp, W * LN, e, s);
+                }
+            }
+#pragma unroll
+            for (int o = LK; o < 32; o <<= 1) {
+#pragma unroll
+                for (int i = 0; i < 2 * J; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            }
+            if (nl == 0) {
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    *reinterpret_cast<double2*>(spart + gw * KPAD + 2 * (kl + LK * j)) =
+                        make_double2(s[2 * j], s[2 * j + 1]);
+            }
+            __syncthreads();
+            double gn[U], en[U];
+            double dsum = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = gt + GT * u;
+                double ss0 = 0.0, ss1 = 0.0;
+                if (k < K) {
+#pragma unroll
+                    for (int q = 0; q < W; q += 2) {
+                        ss0 += spart[q * KPAD + k];
+                        ss1 += spart[(q + 1) * KPAD + k];
+                    }
+                }
+                gn[u] = fma(er[u], ss0 + ss1, alr[u]);                    // :185
+                if (k < K) dsum += fabs(gn[u] - gamr[u]);                 // :187
+            }
+            if (warp_owns) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) en[u] = exp_digamma(gn[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) en[u] = 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) gamr[u] = gn[u];                  // :188
+            ++it;
+            dsum = warp_sum(dsum);
+            if (lane == 0) red[gw] = dsum;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = gt + GT * u;
+                if (k < K) es[k] = en[u];
+            }
+            __syncthreads();
+            dsum = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) dsum += red[w];
+            if (dsum <= tolK || it >= p.max_iter) break;                  // :189-190 / :174
+#pragma unroll
+            for (int u = 0; u < U; ++u) er[u] = en[u];
+        }
+
+        // ---- final pass: phi from the LAST e, scattered with red.global.add.f64 -----------------
+        double lacc = 0.0;
+        for (int r0 = gw * LN; r0 < n; r0 += W * LN) {
+            const int r = r0 + nl;
+            const bool ok = r < n;
+            const int id = rid[r];
+            double b[2 * J];
+            const double part = row_dot<LK, J>(p.Bt + (size_t)id * KP + 2 * kl, e, b);
+            const double c = cnt[r];
+            const double w = ok ? c * rcp_nr(part) : 0.0;
+            if (ok && kl == 0) lacc = fma(c, p.mw[id] + log(part), lacc);
+            double* dst = p.phi_ss + (size_t)id * KP + 2 * kl;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if (ok && kl + LK * j < KP2) {
+                    atomicAdd(dst + 2 * LK * j, w * b[2 * j] * e[2 * j]);                       // :207
+                    if (2 * (kl + LK * j) + 1 < K) atomicAdd(dst + 2 * LK * j + 1, w * b[2 * j + 1] * e[2 * j + 1]);
+                }
+            }
+        }
+        double t1 = lacc, sg = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = gt + GT * u;
+            if (k < K) {
+                const double gk = gamr[u];
+                const double ek = er[u];
+                const double dk = gk - alr[u];
+                t1 += lgamma(gk);                                            // :197
+                if (ek > 0.0 && dk != 0.0) t1 -= log(ek) * dk;
+                sg += gk;
+                p.gamma[(size_t)d * K + k] = gk;                             // :212 / :216
+            }
+        }
+        t1 = warp_sum(t1);
+        sg = warp_sum(sg);
+        if (lane == 0) {
+            red[W + 2 * gw] = t1;
+            red[W + 2 * gw + 1] = sg;
+        }
+        __syncthreads();
+        if (gt == 0) {
+            t1 = 0.0;
+            sg = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                t1 += red[W + 2 * w];
+                sg += red[W + 2 * w + 1];
+            }
+            p.docterm[d] = t1 - lgamma(sg);                                  // - lgamma(sum_k gamma_k), :197
+            p.iters[d] = it;
+        }
+    }
+}
+
+}  // namespace pylda

@@ -117,14 +117,15 @@ __global__ void k_lse_final(const double* pm, const double* ps, int K, int nchun
 
 // Partial sums for the ELBO: per block
 //   [0] sum_d docterm   [1] sum_{w,k} phi*Elt   [2] sum_{w,k} phi*(Elt - lse_k)  (held-out, :204)
-//   [3] sum_d iters     [4] #docs at the iteration cap
-constexpr int NTERMS = 5;
+//   [3] sum_d iters     [4] #docs at the iteration cap     [5] sum_d n_d * iters_d (row-trips: fp64 work)
+constexpr int NTERMS = 6;
 __global__ void k_reduce_terms(const double* __restrict__ phi, const double* __restrict__ Elt,
                                const double* __restrict__ lse, int K, int V, int KP,
-                               const double* __restrict__ docterm, const int* __restrict__ iters, long long D,
-                               int max_iter, int heldout, double* partial) {
+                               const double* __restrict__ docterm, const int* __restrict__ iters,
+                               const long long* __restrict__ row_ptr, long long D, int max_iter, int heldout,
+                               double* partial) {
     __shared__ double sh[32];
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nel = (long long)V * KP;
@@ -144,15 +145,17 @@ __global__ void k_reduce_terms(const double* __restrict__ phi, const double* __r
         const int it = iters[i];
         a3 += (double)it;
         a4 += (it >= max_iter) ? 1.0 : 0.0;
+        a5 += (double)it * (double)(row_ptr[i + 1] - row_ptr[i]);
     }
     a0 = block_sum(a0, sh);
     a1 = block_sum(a1, sh);
     a2 = block_sum(a2, sh);
     a3 = block_sum(a3, sh);
     a4 = block_sum(a4, sh);
+    a5 = block_sum(a5, sh);
     if (threadIdx.x == 0) {
         double* o = partial + (size_t)blockIdx.x * NTERMS;
-        o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3; o[4] = a4;
+        o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3; o[4] = a4; o[5] = a5;
     }
 }
 __global__ void k_reduce_final(const double* partial, int nblocks, int nterms, double* out) {

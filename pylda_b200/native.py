@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -33,6 +33,7 @@ class Stats(ctypes.Structure):
         ("n_estep_launches", ctypes.c_int32),
         ("docs_resident", ctypes.c_int64),
         ("docs_streamed", ctypes.c_int64),
+        ("row_trips", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -197,3 +197,30 @@ def test_error_behaviour(ctx):
         ctx.estep(0, g["eta"], bad)
     with pytest.raises(RuntimeError):
         ctx.set_corpus(0, g["row_ptr"], g["ids"], numpy.zeros_like(g["cts"]))   # counts must be >= 1
+
+
+def test_resident_em_loop_matches_oracle(ctx):
+    """eta stays on the device across EM iterations -- E-step, device M-step
+    (variational_bayes.py:222-226) and the alpha statistics (:232-233) computed from the resident gamma.
+    Three EM iterations against the oracle's learning loop with alpha held fixed."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 30, 900
+    row_ptr, ids, cts = synthetic.synthetic_corpus(120, V, seed=12, length="poisson", mean_len=70)
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    alpha_beta = 1.0 / V
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    ctx.set_model(eta, alpha)
+    for em in range(3):
+        ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6)
+        topic_ref, eta_new, alpha_ss_ref = O.m_step(eta, ref["gamma"], ref["phi_ss"], numpy.full(V, alpha_beta))
+        ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
+        res = ctx.get_results(0, gamma=True, phi=False, alpha_ss=True)
+        topic_ll, eta_dev = ctx.mstep_resident(alpha_beta, want_eta=True)
+        assert max_rel(res["gamma"], ref["gamma"]) <= RTOL
+        assert abs(res["doc_ll"] - ref["doc_ll"]) <= RTOL * abs(ref["doc_ll"])
+        assert max_rel(res["alpha_ss"], alpha_ss_ref) <= RTOL
+        assert abs(topic_ll - topic_ref) <= RTOL * abs(topic_ref)
+        assert max_rel(eta_dev, eta_new) <= RTOL
+        eta = eta_new
