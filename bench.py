@@ -14,7 +14,7 @@ e2e   : docs/s through the reference-facing call pylda_estep with HOST buffers: 
         eta/alpha and D2H of gamma, phi_ss and the ELBO inside the timed region
 state : "cold" = eta0 ~ Gamma(100, 1/100) (EM iteration 1, nearly every document runs to the
         50-trip cap -- the worst case); the JSON also carries the same measurement at a warm
-        state (after 2 EM iterations on the device) under "warm".
+        state (EM iteration 5: four resident EM iterations incl. the alpha update) under "warm".
 
 --impl reference times the CPU restatement of the reference (oracle/estep_oracle.py, same numpy
 call sequence as the reference) on all host cores over a bounded sample of the same corpus.
@@ -268,20 +268,36 @@ def run_product(args):
         barrier()
         return wall, dev, ker, st
 
+    def warm_model(want_eta):
+        """EM iterations 1..4 of variational_bayes.py:239-261 with everything resident: device E-step,
+        device M-step, alpha statistics from the device (summed over ranks by the library) and the
+        reference's Newton update of alpha on the host (K numbers).  Leaves the model of EM iteration 5
+        on the device; returns (eta or None, alpha)."""
+        from pylda_b200.variational_bayes import VariationalBayes
+        shell = VariationalBayes()
+        shell._number_of_topics = K
+        shell._number_of_documents = int(allsum(float(D)))
+        shell._alpha_alpha = alpha.copy()
+        ctx.set_model(eta0, alpha)
+        eta_host = None
+        for em in range(4):
+            ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
+            alpha_ss = ctx.get_results(0, gamma=False, phi=False, alpha_ss=True)["alpha_ss"]
+            _, eta_host = ctx.mstep_resident(alpha_beta, want_eta=(want_eta and em == 3))
+            shell.optimize_hyperparameters(alpha_ss)
+            ctx.set_alpha(shell._alpha_alpha)
+        return eta_host, shell._alpha_alpha.copy()
+
     results = {}
     sampler = ClockSampler(local_rank)
+    alpha_warm = alpha
     for state in ("cold", "warm"):
-        ctx.set_model(eta0, alpha)
         if state == "warm":
-            # two EM iterations on the device: E-step, device M-step (alpha kept fixed)
-            for _ in range(2):
-                ctx.estep_resident(0, 50, 1e-6)
-                ctx.mstep_resident(alpha_beta, want_eta=False)
+            _, alpha_warm = warm_model(False)
+        else:
+            ctx.set_model(eta0, alpha)
         for _ in range(args.warmup):
-            if state == "warm":
-                ctx.estep_resident(0, 50, 1e-6)
-            else:
-                ctx.estep_resident(0, 50, 1e-6)
+            ctx.estep_resident(0, 50, 1e-6)
         if state == args.state:
             sampler.start()
         wall, dev, ker, st = timed_resident(args.steps)
@@ -297,12 +313,9 @@ def run_product(args):
                               at_cap=st["docs_at_cap"])
 
     # ---- e2e: the reference-facing call with host buffers (pinned), at the headline state ----
+    alpha_e2e = alpha
     if args.state == "warm":
-        eta_host = None
-        ctx.set_model(eta0, alpha)
-        for _ in range(2):
-            ctx.estep_resident(0, 50, 1e-6)
-            _, eta_host = ctx.mstep_resident(alpha_beta, want_eta=True)
+        eta_host, alpha_e2e = warm_model(True)
     else:
         eta_host = eta0
     eta_pin = numpy.ascontiguousarray(eta_host)
@@ -312,11 +325,11 @@ def run_product(args):
     for a in (eta_pin, gamma_pin, phi_pin):
         ctx.pin(a)
     e2e_steps = max(2, min(args.steps, 5))
-    ctx.estep(0, eta_pin, alpha, 50, 1e-6, gamma_out=gamma_pin, phi_out=phi_pin)   # warm-up
+    ctx.estep(0, eta_pin, alpha_e2e, 50, 1e-6, gamma_out=gamma_pin, phi_out=phi_pin)   # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = ctx.estep(0, eta_pin, alpha, 50, 1e-6, gamma_out=gamma_pin, phi_out=phi_pin)
+        out = ctx.estep(0, eta_pin, alpha_e2e, 50, 1e-6, gamma_out=gamma_pin, phi_out=phi_pin)
     e2e_wall = time.perf_counter() - t0
     barrier()
     e2e_ms = allmax(1e3 * e2e_wall / e2e_steps)
@@ -342,7 +355,7 @@ def run_product(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_single_core(row_ptr, ids, cts, eta_host, alpha, args.cpu_docs)
+        cpu_base = cpu_baseline_single_core(row_ptr, ids, cts, eta_host, alpha_e2e, args.cpu_docs)
 
     if rank == 0:
         other = "warm" if args.state == "cold" else "cold"
@@ -355,7 +368,7 @@ def run_product(args):
                 "workload": "configs[2]: synthetic D=%d docs per GPU, V=%d, K=%d, Zipf lengths (nnz=%d on rank 0)" % (
                     D, V, K, nnz),
                 "state": args.state + (" (eta0 ~ Gamma(100,0.01), EM iteration 1)" if args.state == "cold"
-                                       else " (after 2 EM iterations)"),
+                                       else " (EM iteration 5: after 4 EM iterations with alpha updates)"),
                 "mean_inner_trips": head["mean_trips"], "docs_at_cap": head["at_cap"],
                 "local_parameter_iteration": 50, "converge_threshold": 1e-6,
                 "l2": "inputs larger than L2 (CSR + gamma + tables = %.1f GB per GPU)" % (

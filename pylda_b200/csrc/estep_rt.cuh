@@ -10,7 +10,8 @@
 // Shared memory keeps e (double buffered), the column partials and -- after the last trip --
 // the c*phi rows that leave by bulk reduce-add (UBLKRED), as before.
 //
-// A group of W warps owns one document of at most W * LN * R rows (LN = 32/LK row lanes);
+// A group of W warps owns one document of at most W * LN * R rows (LN = 32/LK row lanes), row
+// groups dealt round-robin to the warps;
 // longer documents use estep_v2 (shared-memory tile) or the streaming kernel.
 #pragma once
 #include "estep_v2.cuh"
@@ -51,14 +52,17 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
     constexpr int RA = RU > 0 ? RU : 1;
     const int kl = lane % LK, nl = lane / LK;
     const int K = p.K, ST = p.ST, KP2 = p.KP >> 1;
-    const int rbase = gw * LN * R + nl;          // lane's rows: rbase + i*LN
+    // Row groups (LN rows each) are dealt round-robin to the W warps, so that every warp of the
+    // group holds about the same number of rows: lane's rows are (i*W + gw)*LN + nl, i < RU.
+    const int rbase = gw * LN + nl;
+    constexpr int RSTEP = W * LN;
 
     // ---- tile -> registers (once per document) ----------------------------------------------
     double b[RA][2 * J];
     double cw[RA];
 #pragma unroll
     for (int i = 0; i < RU; ++i) {
-        const int r = rbase + i * LN;
+        const int r = rbase + i * RSTEP;
         const double* rowp = tile + (size_t)(r < n ? r : 0) * ST + 2 * kl;   // rows >= n: a valid row with weight 0
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -187,7 +191,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
     double lacc = 0.0;
 #pragma unroll
     for (int i = 0; i < RU; ++i) {
-        const int r = rbase + i * LN;
+        const int r = rbase + i * RSTEP;
         if (r < n && kl == 0) lacc = fma(cw[i], mwr[r] + log(part[i]), lacc);   // sum_n c_n logsumexp_n
     }
 #pragma unroll
@@ -196,7 +200,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
         if (kl + LK * j < KP2) {
 #pragma unroll
             for (int i = 0; i < RU; ++i) {
-                const int r = rbase + i * LN;
+                const int r = rbase + i * RSTEP;
                 if (r < n)
                     *reinterpret_cast<double2*>(tile + (size_t)r * ST + 2 * (kl + LK * j)) =
                         make_double2(w[i] * b[i][2 * j] * ev.x, w[i] * b[i][2 * j + 1] * ev.y);   // c_n phi_nk (:207)
@@ -306,8 +310,9 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
         parity ^= 1u;
         gsync<W>(g);
 
-        // rows of this warp: [gw*LN*R, gw*LN*R + RU*LN)
-        int RU = (n - gw * LN * R + LN - 1) / LN;
+        // row groups of this warp: gw, gw + W, ... below ceil(n / LN)
+        const int NG = (n + LN - 1) / LN;
+        int RU = (NG - gw + W - 1) / W;
         RU = RU < 0 ? 0 : (RU > R ? R : RU);
         double lacc = 0.0;
         int it = 0;
