@@ -1,0 +1,78 @@
+"""Parity at BASELINE.json's full sizes, where the oracle cannot run the whole corpus: size-independent
+properties of the E-step plus oracle parity on a subsample of documents (given eta and alpha the
+per-document results do not depend on the other documents, variational_bayes.py:159-190, so gamma_d of
+the full run must match the oracle run on any subset).  Tolerance 1e-5 relative (north_star)."""
+import numpy
+import pytest
+
+from tests.util import RTOL, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _properties_and_subsample(ctx, D, V, K, length, seed, n_sample, mean_len=100):
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    row_ptr, ids, cts = synthetic.synthetic_corpus(D, V, seed=seed, length=length, mean_len=mean_len)
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    r2, i2, c2 = ctx.get_corpus(0)                                     # token indexing: bit-exact round trip
+    assert numpy.array_equal(r2, row_ptr) and numpy.array_equal(i2, ids) and numpy.array_equal(c2, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6, want_alpha_ss=True)
+    res = ctx.get_results(0, gamma=False, phi=False, iters=True)
+    gamma, phi = out["gamma"], out["phi_ss"]
+    n = numpy.diff(row_ptr)
+    N = numpy.add.reduceat(cts.astype(numpy.float64), row_ptr[:-1])
+    tokens = float(cts.sum())
+    # every phi row sums to 1  =>  sum_k gamma_dk = sum_k alpha_k + N_d ; sum phi_ss = number of tokens
+    assert numpy.allclose(gamma.sum(axis=1), alpha.sum() + N, rtol=1e-11)
+    assert abs(phi.sum() - tokens) <= 1e-9 * tokens
+    assert numpy.all(gamma > 0) and numpy.all(numpy.isfinite(gamma)) and numpy.all(phi >= 0)
+    # column sums of the statistics = corpus frequency of each term (sum_k phi_nk = 1 per token)
+    cf = numpy.bincount(ids, weights=cts.astype(numpy.float64), minlength=V)
+    assert numpy.allclose(phi.sum(axis=0), cf, rtol=1e-9, atol=1e-9)
+    assert res["iters"].min() >= 1 and res["iters"].max() <= 50
+    assert numpy.isfinite(out["doc_ll"]) and out["stats"]["inner_iters"] == int(res["iters"].sum())
+    # alpha statistics from the device == the reference's host formula on the returned gamma (:232-233)
+    import scipy.special as sp
+    blk = slice(0, min(D, 50000))
+    a_host = (sp.psi(gamma[blk]) - sp.psi(gamma[blk].sum(axis=1))[:, None]).sum(axis=0)
+    if D <= 50000:
+        assert max_rel(out["alpha_ss"], a_host) <= 1e-9
+    # oracle parity on a subsample that includes the longest and the shortest documents
+    order = numpy.argsort(n)
+    rs = numpy.random.RandomState(seed)
+    pick = numpy.unique(numpy.concatenate([order[:3], order[-4:], rs.choice(D, n_sample, replace=False)]))
+    sub_rp = numpy.zeros(len(pick) + 1, dtype=numpy.int64)
+    numpy.cumsum(n[pick], out=sub_rp[1:])
+    sub_ids = numpy.concatenate([ids[row_ptr[d]:row_ptr[d + 1]] for d in pick])
+    sub_cts = numpy.concatenate([cts[row_ptr[d]:row_ptr[d + 1]] for d in pick])
+    ref = O.e_step(sub_rp, sub_ids, sub_cts, eta, alpha, 50, 1e-6, return_iters=True)
+    assert max_rel(gamma[pick], ref["gamma"]) <= RTOL
+    assert numpy.mean(res["iters"][pick] == ref["iters"]) >= 0.98
+    # the same subsample run alone on the device reproduces its rows of the full run (order independence)
+    ctx.set_corpus(1, sub_rp, sub_ids, sub_cts)
+    alone = ctx.estep(1, eta, alpha, 50, 1e-6, want_phi=False)
+    assert numpy.array_equal(alone["gamma"], gamma[pick])
+    assert abs(alone["doc_ll"] - ref["doc_ll"]) <= RTOL * abs(ref["doc_ll"])
+    return out
+
+
+def test_config2_full_size(ctx):
+    """BASELINE.json configs[1]: synthetic D=100k, V=10k, K=50, ~100 tokens/doc."""
+    out = _properties_and_subsample(ctx, 100000, 10000, 50, "poisson", 1235, 120)
+    print("config2 stats", out["stats"])
+
+
+def test_config3_full_size(ctx):
+    """BASELINE.json configs[2] (the bench workload): synthetic D=1M, V=100k, K=100, Zipf lengths."""
+    out = _properties_and_subsample(ctx, 1000000, 100000, 100, "zipf", 1236, 60)
+    print("config3 stats", out["stats"])
+
+
+def test_config5_shape_reduced_docs(ctx):
+    """BASELINE.json configs[4] shape at reduced D and V (K=500: four topics per owner thread, the widest
+    lane shape; the full V=1M table is 4 GB per copy and is exercised by the bench, not by a test)."""
+    out = _properties_and_subsample(ctx, 20000, 100000, 500, "poisson", 1238, 24)
+    print("config5-shape stats", out["stats"])
