@@ -182,8 +182,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: synthetic D=%d, V=%d, K=%d, Zipf lengths; EM iteration 1 (eta0)" % (
-            args.docs, V_TYPES, K_TOPICS), "state": "cold"},
+        "config": {"workload": "configs[2]: synthetic D=%d docs per GPU, V=%d, K=%d, Zipf lengths (nnz=%d on rank 0)" % (
+            args.docs, V_TYPES, K_TOPICS, len(ids)),
+            "state": "cold (eta0 ~ Gamma(100,0.01), EM iteration 1)",
+            "mean_inner_trips": sum(iters) / max(1, total_d),
+            "local_parameter_iteration": 50, "converge_threshold": 1e-06,
+            "parallelism": "%d host processes, one document shard each (the reference itself is single-threaded)" % cores,
+            "timing": "wall clock around each bounded sample step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d docs/step (%d per core) of the same corpus, %d worker processes of the numpy "
                                    "restatement of variational_bayes.py:132-216 (the Python-2 reference cannot run "
@@ -396,7 +401,9 @@ def run_product(args):
                     "roofline_frac_read": o["stats"]["algo_read_bytes"] / (o["ker_ms"] * 1e-3) / 1e9 / peak},
             "e2e": {"value": head["docs_total"] / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "elbo_doc_ll": e2e_doc_ll, "host_buffers": "pinned (cudaHostRegister)"},
+                    "elbo_doc_ll": e2e_doc_ll,
+                    "host_buffers": "page-locked (cudaHostRegister, mapped): eta H2D and phi_ss D2H by cudaMemcpyAsync, "
+                                    "gamma stored straight into the host buffer by the kernels (counted in d2h bytes)"},
             "gpu_launches": int(st["n_launches"]) * args.steps,
             "estep_kernel_launches_per_step": int(st["n_estep_launches"]),
             "docs_resident": st["docs_resident"], "docs_streamed": st["docs_streamed"],

@@ -131,8 +131,10 @@ int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double*
 int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]);
 int pylda_comm_init(pylda_ctx* ctx, int n_ranks, int rank, const char id[PYLDA_NCCL_ID_BYTES]);
 
-/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) so that the H2D/D2H copies of
- * pylda_estep run at full PCIe rate.  Optional: pageable buffers work, only slower. */
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister, mapped) so that the H2D/D2H copies of
+ * pylda_estep run at full PCIe rate.  Optional: pageable buffers work, only slower.  When the gamma_DxK
+ * argument of pylda_estep is page-locked (and alpha_ss_K is NULL) the kernels store gamma directly into
+ * it over PCIe while they run, instead of a D x K copy at the end of the call. */
 int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes);
 int pylda_host_unregister(pylda_ctx* ctx, void* ptr);
 

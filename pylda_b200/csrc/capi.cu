@@ -81,6 +81,9 @@ struct Corpus {
     // per-corpus outputs
     double* gamma = nullptr;
     size_t gamma_cap = 0;            // doubles
+    double* gamma_dst = nullptr;     // where the kernels of the current E-step write gamma: `gamma`, or the
+                                     // device alias of a caller's page-locked host buffer (zero-copy D2H)
+    bool gamma_on_device = false;
     double* docterm = nullptr;
     int* iters = nullptr;
     bool has_results = false;
@@ -399,7 +402,7 @@ int launch_estep_v1(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_
         p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
         p.order = cp.order + c.lo; p.ndocs = (int)nd; p.counter = ctx->counters + ci;
         p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-        p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
         p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
         p.W = c.W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = cta_fixed;
         p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
@@ -488,7 +491,7 @@ int launch_streaming(pylda_ctx* ctx, Corpus& cp, long long nd, int LK, int J, in
     p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
     p.order = cp.order; p.ndocs = (int)nd; p.counter = ctx->counters + counter_slot;
     p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-    p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+    p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
     p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
     p.W = 8; p.nmax = 0; p.group_bytes = gl.bytes; p.off_groups = cta_fixed;
     p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
@@ -528,7 +531,7 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
     p.order = cp.order + lo; p.ndocs = (int)nd; p.counter = ctx->counters + counter_slot;
     p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-    p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+    p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
     p.K = K; p.KP = KP; p.ST = KP; p.max_iter = max_iter; p.tol = tol;
     p.W = W; p.nmax = cap; p.group_bytes = gl.bytes;
     p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt; p.off_rid = gl.off_rid;
@@ -635,7 +638,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
                 p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
                 p.order = cp.order + lo; p.ndocs = (int)nd; p.counter = nullptr;
                 p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-                p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+                p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
                 p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
                 p.W = 8; p.nmax = cap_cl; p.group_bytes = gl.bytes; p.off_groups = 0;
                 p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
@@ -708,7 +711,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
         p.order = cp.order + c.lo; p.ndocs = (int)nd; p.counter = ctx->counters + 1 + ci;
         p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-        p.gamma = cp.gamma; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
         p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
         p.W = W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = 0;
         p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
@@ -916,8 +919,18 @@ int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K) {
     return 0;
 }
 
+static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
+                               pylda_stats* stats, double* gamma_host_alias);
+
 int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
                          pylda_stats* stats) {
+    return estep_resident_impl(ctx, slot, max_iter, tol, heldout, want_alpha_ss, stats, nullptr);
+}
+
+// gamma_host_alias: device-visible alias of a page-locked caller buffer; when given, the per-document
+// kernels store gamma straight into it (the D x K copy back disappears from the end of the call)
+static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
+                               pylda_stats* stats, double* gamma_host_alias) {
     if (!ctx) return 1;
     if (slot < 0 || slot > 1) return fail(ctx, "pylda_estep: slot must be 0 or 1");
     if (!ctx->model_set) return fail(ctx, "pylda_estep: no model on the device (pylda_set_model)");
@@ -930,6 +943,8 @@ int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int
     memset(&st, 0, sizeof st);
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;
     if (ensure_outputs(ctx, cp)) return 1;
+    cp.gamma_dst = (gamma_host_alias && !want_alpha_ss) ? gamma_host_alias : cp.gamma;
+    cp.gamma_on_device = (cp.gamma_dst == cp.gamma);
     const int nred = ctx->prop.multiProcessorCount * 2;
     const int nass = ctx->prop.multiProcessorCount * 2;
     if (ensure_partial(ctx, std::max((size_t)nred * NTERMS, std::max((size_t)nass * K, (size_t)2 * 64 * K)))) return 1;
@@ -1002,8 +1017,12 @@ int pylda_get_results(pylda_ctx* ctx, int slot, double* gamma_DxK, double* phi_s
     if (!cp.has_results) return fail(ctx, "pylda_get_results: no E-step results for slot %d", slot);
     CK(cudaSetDevice(ctx->device));
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;
-    if (gamma_DxK && cp.D)
+    if (gamma_DxK && cp.D) {
+        if (!cp.gamma_on_device)
+            return fail(ctx, "pylda_get_results: gamma of the last E-step was written directly to the caller's "
+                             "page-locked buffer and is not on the device");
         CK(cudaMemcpyAsync(gamma_DxK, cp.gamma, (size_t)cp.D * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (phi_ss_KxV) {
         if (!ctx->phi_KV_valid) {
             dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
@@ -1030,8 +1049,18 @@ int pylda_estep(pylda_ctx* ctx, int slot, int K, int V, const double* eta_KxV, c
                 double* words_ll, pylda_stats* stats) {
     if (!ctx) return 1;
     if (pylda_set_model(ctx, K, V, eta_KxV, alpha_K)) return 1;
-    if (pylda_estep_resident(ctx, slot, max_iter, tol, heldout, alpha_ss_K != nullptr, stats)) return 1;
-    return pylda_get_results(ctx, slot, gamma_DxK, phi_ss_KxV, alpha_ss_K, doc_ll, words_ll, nullptr);
+    // page-locked (pylda_host_register / cudaHostAlloc) gamma buffer: let the kernels write into it
+    double* alias = nullptr;
+    if (gamma_DxK && !alpha_ss_K) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, gamma_DxK) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            alias = (double*)at.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    if (estep_resident_impl(ctx, slot, max_iter, tol, heldout, alpha_ss_K != nullptr, stats, alias)) return 1;
+    const bool direct = alias && !ctx->corp[slot].gamma_on_device;
+    return pylda_get_results(ctx, slot, direct ? nullptr : gamma_DxK, phi_ss_KxV, alpha_ss_K, doc_ll, words_ll, nullptr);
 }
 
 int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, double* eta_out_KxV) {
@@ -1104,7 +1133,7 @@ int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes) {
     if (!ctx) return 1;
     if (!ptr || bytes <= 0) return fail(ctx, "pylda_host_register: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
     return 0;
 }
 int pylda_host_unregister(pylda_ctx* ctx, void* ptr) {

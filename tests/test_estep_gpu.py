@@ -224,3 +224,25 @@ def test_resident_em_loop_matches_oracle(ctx):
         assert abs(topic_ll - topic_ref) <= RTOL * abs(topic_ref)
         assert max_rel(eta_dev, eta_new) <= RTOL
         eta = eta_new
+
+
+def test_page_locked_gamma_buffer_is_written_in_place(ctx):
+    """pylda_estep with a page-locked gamma buffer: the kernels store gamma straight into host memory
+    (no D x K copy at the end); results must be identical to the pageable path."""
+    g = load_golden("zipf48_k100")
+    ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
+    plain = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6)
+    D = len(g["row_ptr"]) - 1
+    pinned = numpy.full((D, g["K"]), -1.0)
+    ctx.pin(pinned)
+    try:
+        out = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned)
+        assert out["gamma"] is pinned
+        assert numpy.array_equal(pinned, plain["gamma"])
+        assert out["doc_ll"] == plain["doc_ll"] or abs(out["doc_ll"] - plain["doc_ll"]) <= 1e-12 * abs(plain["doc_ll"])
+        with pytest.raises(RuntimeError):
+            ctx.get_results(0, gamma=True, phi=False)        # gamma of that call is not on the device
+        again = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned, want_alpha_ss=True)   # falls back to the copy
+        assert numpy.array_equal(again["gamma"], plain["gamma"])
+    finally:
+        ctx.unpin(pinned)
