@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 2
+#define PYLDA_ABI_VERSION 3
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -130,6 +130,10 @@ int pylda_special(pylda_ctx* ctx, int which, int64_t n, const double* x, double*
  * the ELBO scalars; gamma stays sharded. */
 int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]);
 int pylda_comm_init(pylda_ctx* ctx, int n_ranks, int rank, const char id[PYLDA_NCCL_ID_BYTES]);
+/* In-place sum over ranks of a host buffer of n doubles (H2D, ncclAllReduce, D2H); a no-op without a
+ * communicator.  Used by the class layer to make rank 0's random eta0 draw (variational_bayes.py:95)
+ * the model of every rank. */
+int pylda_comm_allreduce_sum(pylda_ctx* ctx, double* buf, int64_t n);
 
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister, mapped) so that the H2D/D2H copies of
  * pylda_estep run at full PCIe rate.  Optional: pageable buffers work, only slower.  When the gamma_DxK

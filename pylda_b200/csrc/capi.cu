@@ -1143,6 +1143,22 @@ int pylda_host_unregister(pylda_ctx* ctx, void* ptr) {
     return 0;
 }
 
+int pylda_comm_allreduce_sum(pylda_ctx* ctx, double* buf, int64_t n) {
+    if (!ctx) return 1;
+    if (n < 0 || (n > 0 && !buf)) return fail(ctx, "pylda_comm_allreduce_sum: bad arguments");
+    if (!ctx->comm || n == 0) return 0;              // single rank: the sum over ranks is the input
+    CK(cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    CK(dalloc(&d, (size_t)n));
+    CK(cudaMemcpyAsync(d, buf, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = g_nccl.AllReduce(d, d, (size_t)n, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (rc) { cudaFree(d); return fail(ctx, "ncclAllReduce: %s", g_nccl.GetErrorString(rc)); }
+    CK(cudaMemcpyAsync(buf, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return 0;
+}
+
 int pylda_comm_unique_id(char id_out[PYLDA_NCCL_ID_BYTES]) {
     std::string err;
     if (!load_nccl(&err)) return fail(nullptr, "%s", err.c_str());

@@ -60,11 +60,14 @@ def main(argv=None):
     snapshot_interval = options.snapshot_interval
     inference_mode = options.inference_mode
 
+    # one process per GPU (torchrun): every rank trains, rank 0 owns the output directory
+    from . import distributed
+    rank, world_size, _ = distributed.world()
     input_directory = options.input_directory.rstrip("/")
     corpus_name = os.path.basename(input_directory)
     output_directory = options.output_directory
     for path in (output_directory, os.path.join(output_directory, corpus_name)):
-        if not os.path.exists(path):
+        if rank == 0 and not os.path.exists(path):
             os.mkdir(path)
     output_directory = os.path.join(output_directory, corpus_name)
 
@@ -82,15 +85,17 @@ def main(argv=None):
     suffix += "-lda-I%d-S%d-K%d-aa%f-ab%f-im%d/" % (training_iterations, snapshot_interval, number_of_topics,
                                                     alpha_alpha, alpha_beta, inference_mode)
     output_directory = os.path.join(output_directory, suffix)
-    os.mkdir(os.path.abspath(output_directory))
+    if rank == 0:
+        os.mkdir(os.path.abspath(output_directory))
 
     settings = [("input_directory", input_directory), ("corpus_name", corpus_name),
                 ("training_iterations", "%d" % training_iterations), ("snapshot_interval", str(snapshot_interval)),
                 ("number_of_topics", str(number_of_topics)), ("alpha_alpha", str(alpha_alpha)),
                 ("alpha_beta", str(alpha_beta)), ("inference_mode", "%d" % inference_mode)]
-    with open(output_directory + "option.txt", "w") as f:                                         # :147-162
-        for key, value in settings:
-            f.write("%s=%s\n" % (key, value))
+    if rank == 0:
+        with open(output_directory + "option.txt", "w") as f:                                     # :147-162
+            for key, value in settings:
+                f.write("%s=%s\n" % (key, value))
     rule = "========== ========== ========== ========== =========="
     print(rule)
     print("output_directory=" + output_directory)
@@ -109,12 +114,14 @@ def main(argv=None):
     lda_inferencer._initialize(train_docs, vocab, number_of_topics, alpha_alpha, alpha_beta)       # :194
     for _ in range(training_iterations):                                                           # :196-201
         lda_inferencer.learning()
-        if lda_inferencer._counter % snapshot_interval == 0:
+        if lda_inferencer._counter % snapshot_interval == 0 and rank == 0:
+            # multi-process: beta is global; exp_gamma holds rank 0's document shard
             lda_inferencer.export_beta(output_directory + "exp_beta-" + str(lda_inferencer._counter))
             lda_inferencer.export_gamma(output_directory + "exp_gamma-" + str(lda_inferencer._counter))
-    model_snapshot_path = os.path.join(output_directory, "model-" + str(lda_inferencer._counter))
-    with open(model_snapshot_path, "wb") as f:                                                     # :203-204
-        pickle.dump(lda_inferencer, f)
+    if rank == 0:
+        model_snapshot_path = os.path.join(output_directory, "model-" + str(lda_inferencer._counter))
+        with open(model_snapshot_path, "wb") as f:                                                 # :203-204
+            pickle.dump(lda_inferencer, f)
     return output_directory
 
 

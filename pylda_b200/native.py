@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -65,6 +65,7 @@ _SIGNATURES = {
     "pylda_special": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, _c_double_p, _c_double_p]),
     "pylda_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "pylda_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "pylda_comm_allreduce_sum": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64]),
     "pylda_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "pylda_host_unregister": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "pylda_device_name": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
@@ -257,6 +258,12 @@ class EStepContext(object):
     def comm_init(self, n_ranks, rank, unique_id):
         assert len(unique_id) == NCCL_ID_BYTES
         self._check(self._lib.pylda_comm_init(self._h, int(n_ranks), int(rank), unique_id), "pylda_comm_init")
+
+    def allreduce_sum(self, array):
+        """In-place sum over ranks of a C-contiguous float64 array (no-op on a single rank)."""
+        assert array.dtype == numpy.float64 and array.flags.c_contiguous
+        self._check(self._lib.pylda_comm_allreduce_sum(self._h, _dp(array), array.size), "pylda_comm_allreduce_sum")
+        return array
 
     def pin(self, array):
         """Page-lock a numpy array in place (cudaHostRegister)."""

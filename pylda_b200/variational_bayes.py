@@ -15,7 +15,7 @@ import numpy
 import scipy.special
 
 from .inferencer import Inferencer, compute_dirichlet_expectation
-from . import native
+from . import distributed, native
 
 
 def pack_parsed_corpus(parsed_corpus):
@@ -41,19 +41,44 @@ class VariationalBayes(Inferencer):
         Inferencer.__init__(self, hyper_parameter_optimize_interval)   # :58-67
         self._native = None
         self._train_uploaded = False
+        self._alpha_ss_device = None
 
     # ---- the object must stay picklable (launch_train.py:203-204): drop the device handle ----
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_native"] = None
         state["_train_uploaded"] = False
+        state["_alpha_ss_device"] = None
         return state
 
     def _context(self):
+        """The device context of this process.  Launched as one process per GPU (RANK / WORLD_SIZE /
+        LOCAL_RANK in the environment, e.g. by torchrun) the ranks are joined with NCCL: every rank
+        parses the same corpus, runs the E-step on its own nnz-balanced shard of documents, and the
+        library all-reduces the K x V statistics, the ELBO scalars and the alpha statistics.
+        self._gamma then holds the rows of the local shard only (self._gamma_rows = (lo, hi))."""
         if self._native is None:
-            self._native = native.EStepContext(int(os.environ.get("PYLDA_DEVICE", "0")))
+            rank, size, local = distributed.world()
+            self._native = native.EStepContext(local)
+            self._rank, self._world = rank, size
+            if size > 1:
+                if os.environ.get("PYTHONHASHSEED", "random") == "random":
+                    raise RuntimeError("pylda_b200: multi-process runs need the same PYTHONHASHSEED on every rank "
+                                       "(type ids come from set() iteration order, inferencer.py:63-65)")
+                uid = distributed.exchange_unique_id(rank, size, native.EStepContext.comm_unique_id)
+                self._native.comm_init(size, rank, uid)
             self._train_uploaded = False
         return self._native
+
+    def _shard(self, csr):
+        """(lo, hi, csr shard) of this rank; the whole corpus when single-process."""
+        row_ptr, ids, cts = csr
+        D = len(row_ptr) - 1
+        if getattr(self, "_world", 1) <= 1:
+            return 0, D, csr
+        b = native.shard_bounds(row_ptr, self._world)
+        lo, hi = int(b[self._rank]), int(b[self._rank + 1])
+        return lo, hi, native.shard_csr(row_ptr, ids, cts, lo, hi)
 
     def _initialize(self, corpus, vocab, number_of_topics, alpha_alpha, alpha_beta):
         # :82-95
@@ -66,6 +91,12 @@ class VariationalBayes(Inferencer):
         self._eta = numpy.random.gamma(100., 1. / 100., (self._number_of_topics, self._number_of_types))
         self._train_csr = pack_parsed_corpus(self._parsed_corpus)
         self._train_uploaded = False
+        rank, size, _ = distributed.world()
+        if size > 1:
+            # every rank drew its own eta0; rank 0's draw becomes the model of all ranks
+            if rank != 0:
+                self._eta[:] = 0.0
+            self._context().allreduce_sum(self._eta)
 
     def parse_data(self, corpus):
         # :98-130 -- per document: unique in-vocabulary type ids (first-seen order) and counts;
@@ -98,16 +129,20 @@ class VariationalBayes(Inferencer):
         (words_log_likelihood, gamma_values) and leaves self._gamma untouched."""
         ctx = self._context()
         heldout = parsed_corpus is not None
+        multi = self._world > 1
         if heldout:
             word_ids, word_cts = parsed_corpus[0], parsed_corpus[1]
             assert len(word_ids) == len(word_cts)
-            ctx.set_corpus(1, *pack_parsed_corpus((word_ids, word_cts)))
+            lo, hi, shard = self._shard(pack_parsed_corpus((word_ids, word_cts)))
+            ctx.set_corpus(1, *shard)
             slot, number_of_documents = 1, len(word_ids)
         else:
             if not self._train_uploaded:
                 if getattr(self, "_train_csr", None) is None:
                     self._train_csr = pack_parsed_corpus(self._parsed_corpus)
-                ctx.set_corpus(0, *self._train_csr)
+                lo, hi, shard = self._shard(self._train_csr)
+                ctx.set_corpus(0, *shard)
+                self._gamma_rows = (lo, hi)
                 self._train_uploaded = True
             slot, number_of_documents = 0, len(self._parsed_corpus[0])
         # the reference visits documents in numpy.random.permutation order (:159); the order only
@@ -115,10 +150,11 @@ class VariationalBayes(Inferencer):
         numpy.random.permutation(number_of_documents)
         out = ctx.estep(slot, self._eta, self._alpha_alpha, local_parameter_iteration,
                         local_parameter_converge_threshold, heldout=heldout,
-                        want_gamma=True, want_phi=not heldout)
+                        want_gamma=True, want_phi=not heldout, want_alpha_ss=multi and not heldout)
         self._last_estep_stats = out["stats"]
         if not heldout:
-            self._gamma = out["gamma"]
+            self._gamma = out["gamma"]                 # multi-process: rows self._gamma_rows of the corpus
+            self._alpha_ss_device = out["alpha_ss"]    # summed over ranks by the library (None single-process)
             return out["doc_ll"], out["phi_ss"]
         return out["words_ll"], out["gamma"]
 
@@ -130,9 +166,14 @@ class VariationalBayes(Inferencer):
                                           - scipy.special.gammaln(numpy.sum(self._eta, axis=1)))
         self._eta = phi_sufficient_statistics + self._alpha_beta
         assert self._eta.shape == (self._number_of_topics, self._number_of_types)
-        alpha_sufficient_statistics = scipy.special.psi(self._gamma) \
-            - scipy.special.psi(numpy.sum(self._gamma, axis=1)[:, numpy.newaxis])
-        alpha_sufficient_statistics = numpy.sum(alpha_sufficient_statistics, axis=0)
+        if getattr(self, "_alpha_ss_device", None) is not None:
+            # multi-process: self._gamma is only this rank's shard; the same statistic (:232-233) was
+            # computed on every rank's device from its gamma rows and all-reduced by the library
+            alpha_sufficient_statistics = self._alpha_ss_device
+        else:
+            alpha_sufficient_statistics = scipy.special.psi(self._gamma) \
+                - scipy.special.psi(numpy.sum(self._gamma, axis=1)[:, numpy.newaxis])
+            alpha_sufficient_statistics = numpy.sum(alpha_sufficient_statistics, axis=0)
         return topic_log_likelihood, alpha_sufficient_statistics
 
     def learning(self):
@@ -211,7 +252,7 @@ class VariationalBayes(Inferencer):
         # :343-356
         exp_gamma = self._gamma / numpy.sum(self._gamma, axis=1)[:, numpy.newaxis]
         with open(exp_gamma_path, 'w') as output:
-            for document_index in range(self._number_of_documents):
+            for document_index in range(exp_gamma.shape[0]):     # all documents; the local shard when multi-process
                 fields = []
                 for rank, topic_index in enumerate(reversed(numpy.argsort(exp_gamma[document_index, :])), 1):
                     fields.append("%d:%g" % (topic_index, exp_gamma[document_index, topic_index]))

@@ -74,3 +74,44 @@ def test_two_gpus_equal_one_gpu_and_oracle():
     ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6)
     assert numpy.max(numpy.abs(gamma - ref["gamma"]) / ref["gamma"]) <= 1e-5
     assert abs(one["doc_ll"] - ref["doc_ll"]) <= 1e-5 * abs(ref["doc_ll"])
+
+
+def _train_rank(rank, world, tmp, port):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), PYTHONHASHSEED="0")
+    import numpy
+    from pylda_b200 import launch_train
+    numpy.random.seed(100 + rank)        # different draws on purpose: rank 0's eta0 must win
+    launch_train.main(["--input_directory=%s" % os.path.join(tmp, "toy"), "--output_directory=%s" % os.path.join(tmp, "out"),
+                       "--number_of_topics=6", "--training_iterations=3", "--snapshot_interval=3", "--inference_mode=2"])
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs at least 2 GPUs")
+def test_launch_train_two_processes_matches_one(capfd):
+    """The class / CLI layer as one process per GPU: same ELBO trace as the single-process run."""
+    import re
+    import torch.multiprocessing as mp
+    from pylda_b200 import launch_train, synthetic
+    V = 400
+    row_ptr, ids, cts = synthetic.synthetic_corpus(90, V, seed=14, length="poisson", mean_len=50)
+    docs = synthetic.render_text(row_ptr, ids, cts)
+    if os.environ.get("PYTHONHASHSEED") != "0":
+        pytest.skip("needs PYTHONHASHSEED=0 (type ids come from set() order and must agree across ranks)")
+    with tempfile.TemporaryDirectory() as tmp:
+        os.mkdir(os.path.join(tmp, "toy"))
+        open(os.path.join(tmp, "toy", "train.dat"), "w").write("\n".join(docs) + "\n")
+        open(os.path.join(tmp, "toy", "voc.dat"), "w").write("".join("w%d\t1\n" % i for i in range(V)))
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            os.environ.pop(k, None)
+        numpy.random.seed(100)
+        launch_train.main(["--input_directory=%s" % os.path.join(tmp, "toy"), "--output_directory=%s" % os.path.join(tmp, "single"),
+                           "--number_of_topics=6", "--training_iterations=3", "--snapshot_interval=3", "--inference_mode=2"])
+        single = [float(x) for x in re.findall(r"with log likelihood (\S+)", capfd.readouterr().out)]
+        mp.spawn(_train_rank, args=(2, tmp, 29631), nprocs=2, join=True)
+        multi = [float(x) for x in re.findall(r"with log likelihood (\S+)", capfd.readouterr().out)]
+        run = os.listdir(os.path.join(tmp, "out", "toy"))
+        assert len(run) == 1
+        files = sorted(os.listdir(os.path.join(tmp, "out", "toy", run[0])))
+        assert files == ["exp_beta-3", "exp_gamma-3", "model-3", "option.txt"]
+    assert len(single) == 3 and len(multi) == 6                      # both ranks print every iteration
+    assert sorted(set(multi)) == sorted(set(single))                 # the same 6-digit ELBO values
