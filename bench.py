@@ -317,6 +317,14 @@ def run_product(args):
                               doc_ll=res["doc_ll"], mean_trips=st["inner_iters"] / docs_total,
                               at_cap=st["docs_at_cap"])
 
+    # ---- memory-path probe: the same E-step limited to ONE trip per document (local_parameter_iteration=1):
+    # gather + one fixed-point trip + scatter, i.e. the regime where the HBM roof binds ----
+    ctx.set_model(eta0, alpha)
+    for _ in range(2):
+        ctx.estep_resident(0, 1, 1e-6)
+    probe_ms = sorted(ctx.estep_resident(0, 1, 1e-6)["kernel_ms"] for _ in range(3))[1]
+    probe_ms = allmax(probe_ms)
+
     # ---- e2e: the reference-facing call with host buffers (pinned), at the headline state ----
     alpha_e2e = alpha
     if args.state == "warm":
@@ -399,6 +407,10 @@ def run_product(args):
                     "mean_inner_trips": o["mean_trips"], "elbo_doc_ll": o["doc_ll"],
                     "roofline_frac": o["stats"]["algo_total_bytes"] / (o["ker_ms"] * 1e-3) / 1e9 / peak,
                     "roofline_frac_read": o["stats"]["algo_read_bytes"] / (o["ker_ms"] * 1e-3) / 1e9 / peak},
+            "probe_1trip": {"what": "same corpus with local_parameter_iteration=1 (gather + one trip + scatter): the "
+                                    "regime where the HBM roof binds", "kernel_ms": probe_ms,
+                            "achieved": algo / (probe_ms * 1e-3) / 1e9, "unit": "GB/s",
+                            "frac": algo / (probe_ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": head["docs_total"] / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "elbo_doc_ll": e2e_doc_ll,
