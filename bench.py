@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0
 
 
@@ -424,7 +424,7 @@ def run_product(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -432,7 +432,34 @@ def run_product(args):
     return 0
 
 
+class StdoutGuard(object):
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its
+    version banner to stdout at communicator creation), so fd 1 is pointed at stderr for the whole
+    run and the JSON line goes to the saved, real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(line):
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
