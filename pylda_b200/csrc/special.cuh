@@ -95,25 +95,48 @@ __constant__ double c_g[9] = {0x1.72c2625e26025p-2, -0x1.ab037fd41fbcdp-3, 0x1.1
                               0x1.e1ae396a755f1p-8, -0x1.0315dff6af42ap-8, 0x1.d1a17ce364565p-9, -0x1.a4fa4f9f36231p-8,
                               0x1.55555555553dap-5};
 
-// exp(y) for y <= 0, branch-free: y = n ln2 + r, degree-11 polynomial, exponent patched in.
-// Results below 2^-1020 are flushed to 0 (the reference's exp() would return a denormal there;
-// such e_k are 300 orders of magnitude below anything that reaches gamma, phi or the ELBO).
+// exp(y) for y <= 0, branch-free: y = n ln2 + r, degree-11 polynomial (Estrin form: the block-level
+// ncu view showed the exp(psi) code 61 % in fixed-latency dependency waits -- register pressure keeps
+// ptxas from interleaving the four evaluations of a lane, so the parallelism has to be inside one),
+// exponent patched in.  Results below 2^-1020 are flushed to 0 (the reference's exp() would return
+// a denormal there; such e_k are 300 orders of magnitude below anything that reaches gamma, phi or
+// the ELBO).
 __device__ __forceinline__ double exp_nonpos(double y) {
     const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52: n lands in the low word of t
     const double t = fma(y, 0x1.71547652b82fep+0, SHIFT);
     const double n = t - SHIFT;
     double r = fma(n, -0x1.62e42fefa39efp-1, y);
     r = fma(n, -0x1.abc9e3b39803fp-56, r);
-    double p = c_exp[11];
-#pragma unroll
-    for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp[i]);
+    const double r2 = r * r;
+    const double a0 = fma(c_exp[1], r, c_exp[0]);
+    const double a1 = fma(c_exp[3], r, c_exp[2]);
+    const double a2 = fma(c_exp[5], r, c_exp[4]);
+    const double a3 = fma(c_exp[7], r, c_exp[6]);
+    const double a4 = fma(c_exp[9], r, c_exp[8]);
+    const double a5 = fma(c_exp[11], r, c_exp[10]);
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double p = fma(fma(b2, r4, b1), r4, b0);
     const int ni = __double2loint(t);
     const double res = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
     return y < -707.0 ? 0.0 : res;
 }
 
+// 1/x with ONE cubic Newton step on the MUFU.RCP64H seed: r (1 + e + e^2), e = 1 - x r; the seed has
+// >= 20 good bits, so the result is good to 2^-60 with a 3-deep dependency chain instead of 4.
+__device__ __forceinline__ double rcp_cubic(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(r, e2, r);
+}
+
 // exp(psi(x)) for x > 0 (x >= 1e-300): same construction as exp_digamma_shifted with c = 0, the
-// Newton reciprocal and the branch-free exp.  Underflows to 0 where exp(psi(x)) < 1e-307 (x <~ 1.4e-3).
+// Newton reciprocal and the branch-free exp, both polynomials in Estrin form.  Underflows to 0 where
+// exp(psi(x)) < 1e-307 (x <~ 1.4e-3).
 __device__ __forceinline__ double exp_digamma(double x) {
     const double x1 = x + 1.0, x2 = x + 2.0, x3 = x + 3.0;
     const double a = x * x1, da = x + x1;
@@ -121,15 +144,23 @@ __device__ __forceinline__ double exp_digamma(double x) {
     const double P = a * b;
     const double Q = fma(da, b, a * db);
     const double z = x + 3.5;
-    const double r = rcp_nr(P * z);
+    const double r = rcp_cubic(P * z);
     const double invz = r * P;
     const double qp = Q * (r * z);
+    const double ex = exp_nonpos(-qp);
     const double u = invz * invz;
-    double g = c_g[0];
-#pragma unroll
-    for (int i = 1; i < 9; ++i) g = fma(g, u, c_g[i]);
+    // g(u) = sum_i c_g[8-i] u^i, degree 8
+    const double u2 = u * u;
+    const double g01 = fma(c_g[7], u, c_g[8]);
+    const double g23 = fma(c_g[5], u, c_g[6]);
+    const double g45 = fma(c_g[3], u, c_g[4]);
+    const double g67 = fma(c_g[1], u, c_g[2]);
+    const double u4 = u2 * u2;
+    const double h0 = fma(g23, u2, g01);
+    const double h1 = fma(g67, u2, g45);
+    const double g = fma(fma(c_g[0], u4, h1), u4, h0);
     const double G = fma(invz, g, z);
-    return G * exp_nonpos(-qp);
+    return G * ex;
 }
 
 // Same function with the coefficients as instruction immediates and the library exp(): more
