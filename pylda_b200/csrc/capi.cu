@@ -579,7 +579,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             if (!fn) continue;
             const int cap = c.W * ln * R;
             const GroupLayout gl = group_layout_rt(c.W, lk, kpad, cap, ST);
-            if (c.G * gl.bytes > smem_budget) continue;
+            if (c.G * gl.bytes + align_up(kpad * 8, 128) > smem_budget) continue;
             cls.push_back({1, c.W, c.G, cap, lk, j, fn, 0, 0});
         }
     }
@@ -698,7 +698,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         }
         if (G < 1) return fail(ctx, "internal: class %d needs %d B of shared memory per group", ci, gl.bytes);
         G = (int)std::min<long long>(G, nd);
-        const int smem = G * gl.bytes;
+        const int smem = G * gl.bytes + (c.kind == 1 ? align_up(kpad * 8, 128) : 0);   // rt: + the CTA's alpha copy
         const int threads = G * W * 32;
         CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
@@ -713,7 +713,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
         p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
         p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
-        p.W = W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = 0;
+        p.W = W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = G * gl.bytes;
         p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
         p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
         void* args[] = {&p};

@@ -44,9 +44,7 @@ struct RtCfg {
 template <int LK, int J, int W, int RU>
 __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* spart, double* red, const double* cnt,
                                         const double* mwr, double* tile, int n, int g, int gt, int gw, int lane,
-                                        bool warp_owns, const double (&alr)[RtCfg<LK, J, W>::U],
-                                        double (&gamr)[RtCfg<LK, J, W>::U], double (&er)[RtCfg<LK, J, W>::U],
-                                        double& lacc_out) {
+                                        bool warp_owns, const double* als, double* gams, double& lacc_out) {
     using C = RtCfg<LK, J, W>;
     constexpr int LN = C::LN, R = C::R, KPAD = C::KPAD, GT = C::GT, U = C::U, NB = C::NB, NP = C::NP;
     constexpr int RA = RU > 0 ? RU : 1;
@@ -59,7 +57,6 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
 
     // ---- tile -> registers (once per document) ----------------------------------------------
     double b[RA][2 * J];
-    double cw[RA];
 #pragma unroll
     for (int i = 0; i < RU; ++i) {
         const int r = rbase + i * RSTEP;
@@ -70,7 +67,6 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
             b[i][2 * j] = v.x;
             b[i][2 * j + 1] = v.y;
         }
-        cw[i] = cnt[r];                          // staged as 0 for rows >= n
     }
 
     double w[RA], part[RA];
@@ -99,7 +95,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
             for (int i = 0; i < RU; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
         }
 #pragma unroll
-        for (int i = 0; i < RU; ++i) w[i] = cw[i] * rcp_nr(part[i]);
+        for (int i = 0; i < RU; ++i) w[i] = cnt[rbase + i * RSTEP] * rcp_nr(part[i]);   // counts: staged as 0 for rows >= n
         // column partial sums of this lane -> (butterfly over NB row-lane bits) -> shared memory.
         // JB topic pairs at a time, rows in the outer loop: 2*JB independent accumulation chains.
         constexpr int JB = 1;
@@ -150,18 +146,23 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                     if (q + 3 < NP) ss3 += spart[(q + 3) * KPAD + k];
                 }
             }
-            gn[u] = fma(er[u], (ss0 + ss1) + (ss2 + ss3), alr[u]);
-            if (k < K) dsum += fabs(gn[u] - gamr[u]);
+            // alpha_k and gamma_k live in shared memory, not registers: the tile already takes 4*J*R
+            // registers per lane and the exp(psi) evaluations below need the rest to overlap
+            const double al = (k < K) ? als[k] : 1.0;
+            const double ek = (k < K) ? es[k] : 0.0;                     // e_k of THIS trip (current buffer)
+            gn[u] = fma(ek, (ss0 + ss1) + (ss2 + ss3), al);
+            if (k < K) {
+                dsum += fabs(gn[u] - gams[k]);
+                gams[k] = gn[u];                                         // :188
+            }
         }
         if (warp_owns) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) en[u] = (W == 1) ? exp_digamma(gn[u]) : exp_digamma_imm(gn[u]);
+            for (int u = 0; u < U; ++u) en[u] = exp_digamma(gn[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) en[u] = 0.0;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) gamr[u] = gn[u];                     // :188
         ++it;
         {
             double* esn = es2 + (it & 1) * KPAD;                         // the buffer the NEXT trip reads
@@ -182,8 +183,6 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
             __syncwarp();
         }
         if (dsum <= tolK || it >= p.max_iter) break;                     // :189-190 / :174
-#pragma unroll
-        for (int u = 0; u < U; ++u) er[u] = en[u];
     }
 
     // ---- phi from the LAST e (buffer (it-1)&1; w[] and part[] are those of the last trip) -------
@@ -192,7 +191,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
 #pragma unroll
     for (int i = 0; i < RU; ++i) {
         const int r = rbase + i * RSTEP;
-        if (r < n && kl == 0) lacc = fma(cw[i], mwr[r] + log(part[i]), lacc);   // sum_n c_n logsumexp_n
+        if (r < n && kl == 0) lacc = fma(cnt[r], mwr[r] + log(part[i]), lacc);   // sum_n c_n logsumexp_n
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -242,14 +241,13 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
     }
     __syncthreads();
 
-    double alr[U], gamr[U], er[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int k = gt + GT * u;
-        alr[u] = (k < K) ? p.alpha[k] : 1.0;
-        gamr[u] = 1.0;
-        er[u] = 0.0;
-    }
+    // alpha: one copy per CTA behind the groups; gamma_k of the group's document: in the slack behind
+    // its tile (finite values, which is all the over-read of the last tile row needs)
+    double* als = reinterpret_cast<double*>(smem_raw + p.off_groups);
+    double* gams = tile + (size_t)CAP * ST;
+    for (int k = tid; k < KPAD; k += blockDim.x) als[k] = (k < K) ? p.alpha[k] : 1.0;
+    __syncthreads();
+
     const bool warp_owns = gw * 32 < K;
     uint32_t parity = 0;
     int nxt = 0;
@@ -295,15 +293,14 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
             for (int x = 0; x < W; ++x) Nd += red[x];
         }
         const double g0 = Nd / (double)K;                  // gamma0 = alpha + N_d / K   (:165)
-#pragma unroll
-        for (int u = 0; u < U; ++u) gamr[u] = alr[u] + g0;
         if (warp_owns) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) er[u] = (W == 1) ? exp_digamma(gamr[u]) : exp_digamma_imm(gamr[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = gt + GT * u;
-                if (k < K) es2[k] = er[u];
+                const double g00 = ((k < K) ? als[k] : 1.0) + g0;
+                if (k < K) gams[k] = g00;
+                const double e0 = exp_digamma(g00);
+                if (k < K) es2[k] = e0;
             }
         }
         mbar_wait(mbar, parity);
@@ -319,8 +316,8 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
 #define PYLDA_RT_CASE(X)                                                                                     \
     case X:                                                                                                  \
         if constexpr (X <= R)                                                                                \
-            it = rt_trips<LK, J, W, X>(p, es2, spart, red, cnt, mwr, tile, n, g, gt, gw, lane, warp_owns, alr, \
-                                       gamr, er, lacc);                                                      \
+            it = rt_trips<LK, J, W, X>(p, es2, spart, red, cnt, mwr, tile, n, g, gt, gw, lane, warp_owns, als, \
+                                       gams, lacc);                                                          \
         break;
         switch (RU) {
             PYLDA_RT_CASE(0) PYLDA_RT_CASE(1) PYLDA_RT_CASE(2) PYLDA_RT_CASE(3) PYLDA_RT_CASE(4)
@@ -335,9 +332,9 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
         for (int u = 0; u < U; ++u) {
             const int k = gt + GT * u;
             if (k < K) {
-                const double gk = gamr[u];
-                const double ek = er[u];
-                const double dk = gk - alr[u];
+                const double gk = gams[k];
+                const double ek = es2[((it - 1) & 1) * KPAD + k];           // e of the last trip
+                const double dk = gk - als[k];
                 t1 += lgamma(gk);                                            // :197
                 if (ek > 0.0 && dk != 0.0) t1 -= log(ek) * dk;               // - sum_k psi_k sum_n c_n phi_nk
                 sg += gk;
