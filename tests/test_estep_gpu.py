@@ -246,3 +246,26 @@ def test_page_locked_gamma_buffer_is_written_in_place(ctx):
         assert numpy.array_equal(again["gamma"], plain["gamma"])
     finally:
         ctx.unpin(pinned)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_sweep(ctx, seed):
+    """Randomised sweep over the number of topics (every compiled lane shape and owner width), corpus
+    shape (incl. documents long enough for the streaming path) and asymmetric alpha."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    rs = numpy.random.RandomState(1000 + seed)
+    K = int(rs.choice([1, 2, 5, 7, 11, 20, 31, 33, 48, 57, 80, 96, 97, 104, 105, 112, 130, 160, 256, 300]))
+    V = int(rs.randint(max(40, K), 1500))
+    D = int(rs.randint(3, 40))
+    length = "zipf" if rs.rand() < 0.5 else "poisson"
+    row_ptr, ids, cts = synthetic.synthetic_corpus(D, V, seed=seed, length=length, mean_len=int(rs.randint(5, 400)))
+    eta = rs.gamma(rs.choice([0.05, 1.0, 100.0]), 1.0, (K, V)) + 1e-3
+    alpha = rs.uniform(0.01, 1.5, K)
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6, heldout=True, return_iters=True)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6, heldout=True)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "seed=%d K=%d V=%d D=%d" % (seed, K, V, D))
+    assert abs(out["words_ll"] - ref["words_ll"]) <= RTOL * abs(ref["words_ll"])
+    it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    assert numpy.mean(it == ref["iters"]) >= 0.9
