@@ -269,3 +269,27 @@ def test_random_shapes_sweep(ctx, seed):
     assert abs(out["words_ll"] - ref["words_ll"]) <= RTOL * abs(ref["words_ll"])
     it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
     assert numpy.mean(it == ref["iters"]) >= 0.9
+
+
+def test_pathologically_long_document(ctx):
+    """A document with more distinct terms than the streaming kernel can index from shared memory
+    (~9000) falls back to the first-generation streaming kernel; same results."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 8, 16000
+    n_long = 12000
+    rs = numpy.random.RandomState(4)
+    long_ids = numpy.sort(rs.choice(V, n_long, replace=False)).astype(numpy.int32)
+    long_cts = rs.randint(1, 4, n_long).astype(numpy.int32)
+    a = synthetic.synthetic_corpus(20, V, seed=3, length="poisson", mean_len=60)
+    row_ptr = numpy.concatenate([a[0], [a[0][-1] + n_long]]).astype(numpy.int64)
+    ids = numpy.concatenate([a[1], long_ids])
+    cts = numpy.concatenate([a[2], long_cts])
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 0.3)
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6, return_iters=True)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "long document")
+    assert out["stats"]["docs_streamed"] >= 1
+    assert out["stats"]["n_estep_launches"] >= 2
