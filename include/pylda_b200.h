@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 3
+#define PYLDA_ABI_VERSION 4
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -141,6 +141,20 @@ int pylda_comm_allreduce_sum(pylda_ctx* ctx, double* buf, int64_t n);
  * it over PCIe while they run, instead of a D x K copy at the end of the call. */
 int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes);
 int pylda_host_unregister(pylda_ctx* ctx, void* ptr);
+
+/* Host-side corpus ingestion (no device involved): the native counterpart of VariationalBayes.parse_data
+ * (variational_bayes.py:98-130).  `text` holds one document per '\n'-terminated line, `vocab` one word per
+ * '\n'-separated line in type-id order (self._index_to_type).  Tokens are split on ASCII whitespace exactly
+ * like str.split(); out-of-vocabulary tokens are skipped (:107-108); per document the distinct type ids
+ * come in first-seen order with their counts (:110-113); documents without an in-vocabulary token are
+ * dropped (:115-117).  n_threads <= 0: all host threads.  The result is read back with pylda_parsed_dims /
+ * pylda_parsed_copy (row_ptr[D+1] int64, ids[nnz] int32, cts[nnz] int32) and released with pylda_parsed_free. */
+typedef struct pylda_parsed pylda_parsed;
+int pylda_parse_corpus(const char* text, int64_t text_len, const char* vocab, int64_t vocab_len, int n_threads,
+                       pylda_parsed** out);
+int pylda_parsed_dims(const pylda_parsed* p, int64_t* D, int64_t* nnz, int64_t* dropped);
+int pylda_parsed_copy(const pylda_parsed* p, int64_t* row_ptr, int32_t* ids, int32_t* cts);
+int pylda_parsed_free(pylda_parsed* p);
 
 /* Introspection for benches/tests. */
 int pylda_device_name(pylda_ctx* ctx, char* out, int cap);

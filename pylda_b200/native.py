@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -68,6 +68,11 @@ _SIGNATURES = {
     "pylda_comm_allreduce_sum": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64]),
     "pylda_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "pylda_host_unregister": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pylda_parse_corpus": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_void_p)]),
+    "pylda_parsed_dims": (ctypes.c_int, [ctypes.c_void_p, _c_int64_p, _c_int64_p, _c_int64_p]),
+    "pylda_parsed_copy": (ctypes.c_int, [ctypes.c_void_p, _c_int64_p, _c_int32_p, _c_int32_p]),
+    "pylda_parsed_free": (ctypes.c_int, [ctypes.c_void_p]),
     "pylda_device_name": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "pylda_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
 }
@@ -281,6 +286,37 @@ class EStepContext(object):
 
     def sm_count(self):
         return self._lib.pylda_sm_count(self._h)
+
+
+def parse_corpus(corpus, index_to_type, n_threads=0):
+    """Native text -> CSR (pylda_parse_corpus): corpus = iterable of document strings, index_to_type =
+    {type id: word}.  Returns (row_ptr, ids, cts, dropped) or None when the text is not pure ASCII
+    (str.split() then also splits on Unicode spaces, which only the Python path reproduces).  Host code,
+    no device needed."""
+    lib = load_library()
+    try:
+        text = ("\n".join(corpus) + "\n").encode("ascii") if len(corpus) else b""
+        vocab = "\n".join(index_to_type[i] for i in range(len(index_to_type))).encode("ascii")
+    except UnicodeEncodeError:
+        return None
+    if b"\n" in vocab and len(vocab.split(b"\n")) != len(index_to_type):
+        return None
+    if text.count(b"\n") != len(corpus):          # a document with an embedded newline: leave it to Python
+        return None
+    h = ctypes.c_void_p()
+    if lib.pylda_parse_corpus(text, len(text), vocab, len(vocab), int(n_threads), ctypes.byref(h)) != 0:
+        raise RuntimeError("pylda_parse_corpus failed")
+    try:
+        D, nnz, dropped = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        lib.pylda_parsed_dims(h, ctypes.byref(D), ctypes.byref(nnz), ctypes.byref(dropped))
+        row_ptr = numpy.empty(D.value + 1, dtype=numpy.int64)
+        ids = numpy.empty(nnz.value, dtype=numpy.int32)
+        cts = numpy.empty(nnz.value, dtype=numpy.int32)
+        lib.pylda_parsed_copy(h, row_ptr.ctypes.data_as(_c_int64_p), ids.ctypes.data_as(_c_int32_p),
+                              cts.ctypes.data_as(_c_int32_p))
+    finally:
+        lib.pylda_parsed_free(h)
+    return row_ptr, ids, cts, int(dropped.value)
 
 
 def shard_bounds(row_ptr, n_ranks):

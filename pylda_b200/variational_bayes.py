@@ -89,7 +89,8 @@ class VariationalBayes(Inferencer):
             + self._alpha_alpha[numpy.newaxis, :] + 1.0 * self._number_of_types / self._number_of_topics
         # the only random draw that affects VB results (:95); same global-RNG call as the reference
         self._eta = numpy.random.gamma(100., 1. / 100., (self._number_of_topics, self._number_of_types))
-        self._train_csr = pack_parsed_corpus(self._parsed_corpus)
+        csr = self.__dict__.pop("_last_parsed_csr", None)      # the native parser already produced the CSR
+        self._train_csr = csr if csr is not None else pack_parsed_corpus(self._parsed_corpus)
         self._train_uploaded = False
         rank, size, _ = distributed.world()
         if size > 1:
@@ -101,6 +102,23 @@ class VariationalBayes(Inferencer):
     def parse_data(self, corpus):
         # :98-130 -- per document: unique in-vocabulary type ids (first-seen order) and counts;
         # documents with no in-vocabulary token are dropped with a warning.
+        # Fast path: the native parser of the C ABI (pylda_parse_corpus, multi-threaded host code, same
+        # semantics bit for bit); the loop below remains for non-ASCII text and as its specification.
+        if os.environ.get("PYLDA_NATIVE_PARSE", "1") != "0" and isinstance(corpus, (list, tuple)):
+            parsed = native.parse_corpus(corpus, self._index_to_type)
+            if parsed is not None:
+                row_ptr, ids, cts, dropped = parsed
+                for _ in range(dropped):
+                    sys.stderr.write("warning: document collapsed during parsing")
+                ids64, cts64 = ids.astype(numpy.int64), cts.astype(numpy.int64)
+                bounds = row_ptr[1:-1]
+                word_ids = numpy.split(ids64, bounds) if len(row_ptr) > 1 else []
+                word_cts = [c[numpy.newaxis, :] for c in numpy.split(cts64, bounds)] if len(row_ptr) > 1 else []
+                for done in range(10000, len(word_ids) + 1, 10000):
+                    print("successfully parse %d documents..." % done)
+                print("successfully parse %d documents..." % len(word_ids))
+                self._last_parsed_csr = (row_ptr, ids, cts)
+                return (word_ids, word_cts)
         doc_count = 0
         word_ids, word_cts = [], []
         lookup = self._type_to_index
