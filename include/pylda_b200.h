@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 4
+#define PYLDA_ABI_VERSION 5
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -112,6 +112,8 @@ int pylda_get_results(pylda_ctx* ctx, int slot, double* gamma_DxK, double* phi_s
  * topic_ll from the OLD eta, then eta <- phi_ss + alpha_beta (scalar prior, inferencer.py:58).
  * eta stays on the device for the next pylda_estep_resident; eta_out_KxV is nullable. */
 int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, double* eta_out_KxV);
+/* Copy the resident eta (K, V) back to the host (after resident EM iterations). */
+int pylda_get_eta(pylda_ctx* ctx, double* eta_KxV);
 /* Replace alpha on the device (after the host Newton update, variational_bayes.py:277-324). */
 int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K);
 

@@ -1090,6 +1090,15 @@ int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, do
     return 0;
 }
 
+int pylda_get_eta(pylda_ctx* ctx, double* eta_KxV) {
+    if (!ctx) return 1;
+    if (!ctx->model_set || !eta_KxV) return fail(ctx, "pylda_get_eta: no model on the device");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(eta_KxV, ctx->eta, (size_t)ctx->K * ctx->V * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int pylda_dirichlet_expectation(pylda_ctx* ctx, int K, int V, const double* eta_KxV, double* out_KxV) {
     if (!ctx) return 1;
     if (K < 1 || V < 1 || !eta_KxV || !out_KxV) return fail(ctx, "pylda_dirichlet_expectation: bad arguments");

@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pylda_get_results": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p,
                                          _c_double_p, _c_double_p, _c_int32_p]),
     "pylda_mstep_resident": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, _c_double_p, _c_double_p]),
+    "pylda_get_eta": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "pylda_set_alpha": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "pylda_dirichlet_expectation": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                                    _c_double_p, _c_double_p]),
@@ -234,6 +235,11 @@ class EStepContext(object):
         self._check(self._lib.pylda_mstep_resident(self._h, float(alpha_beta), ctypes.byref(t), _dp(eta)),
                     "pylda_mstep_resident")
         return t.value, eta
+
+    def get_eta(self):
+        eta = numpy.empty((self.K, self.V), dtype=numpy.float64)
+        self._check(self._lib.pylda_get_eta(self._h, _dp(eta)), "pylda_get_eta")
+        return eta
 
     # -- helpers exposed for parity tests -----------------------------------------------------
     def dirichlet_expectation(self, eta):

@@ -43,12 +43,45 @@ class VariationalBayes(Inferencer):
         self._train_uploaded = False
         self._alpha_ss_device = None
 
+    # ---- self._eta / self._gamma: plain attributes for every caller, but after a resident EM
+    # iteration (learning() below) the current values live in HBM and are copied back only when
+    # somebody reads them (export_*, pickling, a direct e_step call) ----
+    @property
+    def _eta(self):
+        d = self.__dict__
+        if d.get("_eta_stale") and d.get("_native") is not None:
+            d["_eta_host"] = d["_native"].get_eta()
+            d["_eta_stale"] = False
+        return d.get("_eta_host")
+
+    @_eta.setter
+    def _eta(self, value):
+        d = self.__dict__
+        d["_eta_host"] = value
+        d["_eta_stale"] = False
+        d["_model_on_device"] = False          # the device copy (if any) is no longer the model
+
+    @property
+    def _gamma(self):
+        d = self.__dict__
+        if d.get("_gamma_stale") and d.get("_native") is not None:
+            d["_gamma_host"] = d["_native"].get_results(0, gamma=True, phi=False)["gamma"]
+            d["_gamma_stale"] = False
+        return d.get("_gamma_host")
+
+    @_gamma.setter
+    def _gamma(self, value):
+        self.__dict__["_gamma_host"] = value
+        self.__dict__["_gamma_stale"] = False
+
     # ---- the object must stay picklable (launch_train.py:203-204): drop the device handle ----
     def __getstate__(self):
+        self._eta, self._gamma = self._eta, self._gamma        # bring the current values to the host
         state = dict(self.__dict__)
         state["_native"] = None
         state["_train_uploaded"] = False
         state["_alpha_ss_device"] = None
+        state["_model_on_device"] = False
         return state
 
     def _context(self):
@@ -69,6 +102,15 @@ class VariationalBayes(Inferencer):
                 self._native.comm_init(size, rank, uid)
             self._train_uploaded = False
         return self._native
+
+    def _upload_train(self, ctx):
+        if not self._train_uploaded:
+            if getattr(self, "_train_csr", None) is None:
+                self._train_csr = pack_parsed_corpus(self._parsed_corpus)
+            lo, hi, shard = self._shard(self._train_csr)
+            ctx.set_corpus(0, *shard)
+            self._gamma_rows = (lo, hi)
+            self._train_uploaded = True
 
     def _shard(self, csr):
         """(lo, hi, csr shard) of this rank; the whole corpus when single-process."""
@@ -155,13 +197,7 @@ class VariationalBayes(Inferencer):
             ctx.set_corpus(1, *shard)
             slot, number_of_documents = 1, len(word_ids)
         else:
-            if not self._train_uploaded:
-                if getattr(self, "_train_csr", None) is None:
-                    self._train_csr = pack_parsed_corpus(self._parsed_corpus)
-                lo, hi, shard = self._shard(self._train_csr)
-                ctx.set_corpus(0, *shard)
-                self._gamma_rows = (lo, hi)
-                self._train_uploaded = True
+            self._upload_train(ctx)
             slot, number_of_documents = 0, len(self._parsed_corpus[0])
         # the reference visits documents in numpy.random.permutation order (:159); the order only
         # changes fp summation order, but the draw keeps the global RNG stream in step with it
@@ -170,6 +206,7 @@ class VariationalBayes(Inferencer):
                         local_parameter_converge_threshold, heldout=heldout,
                         want_gamma=True, want_phi=not heldout, want_alpha_ss=multi and not heldout)
         self._last_estep_stats = out["stats"]
+        self.__dict__["_model_on_device"] = False      # pylda_estep re-uploads eta/alpha from the host
         if not heldout:
             self._gamma = out["gamma"]                 # multi-process: rows self._gamma_rows of the corpus
             self._alpha_ss_device = out["alpha_ss"]    # summed over ranks by the library (None single-process)
@@ -194,8 +231,47 @@ class VariationalBayes(Inferencer):
             alpha_sufficient_statistics = numpy.sum(alpha_sufficient_statistics, axis=0)
         return topic_log_likelihood, alpha_sufficient_statistics
 
+    def _resident_ok(self):
+        """Resident EM is used when nothing in the subclass changes the E/M-step and the topic prior is
+        the reference's uniform vector (inferencer.py:58); PYLDA_RESIDENT=0 forces the host M-step."""
+        return (os.environ.get("PYLDA_RESIDENT", "1") != "0"
+                and type(self).e_step is VariationalBayes.e_step and type(self).m_step is VariationalBayes.m_step
+                and numpy.all(self._alpha_beta == self._alpha_beta[0]))
+
+    def _learning_resident(self):
+        """learning() with the model resident in HBM: device E-step, device
+        M-step (:222-226), alpha statistics (:232-233) from the device, the reference's Newton update of
+        alpha on the host (K numbers).  No K x V or D x K array crosses PCIe; eta and gamma are fetched
+        lazily when read.  Same arithmetic, same printed line."""
+        self._counter += 1
+        clock_e_step = time.time()
+        ctx = self._context()
+        self._upload_train(ctx)
+        if not self.__dict__.get("_model_on_device"):
+            ctx.set_model(self._eta, self._alpha_alpha)
+        numpy.random.permutation(len(self._parsed_corpus[0]))          # RNG stream of :159
+        self._last_estep_stats = ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
+        res = ctx.get_results(0, gamma=False, phi=False, alpha_ss=True)
+        clock_e_step = time.time() - clock_e_step
+        clock_m_step = time.time()
+        topic_log_likelihood, _ = ctx.mstep_resident(float(self._alpha_beta[0]), want_eta=False)
+        d = self.__dict__
+        d["_eta_stale"] = d["_gamma_stale"] = True
+        d["_model_on_device"] = True
+        self._alpha_ss_device = res["alpha_ss"] if self._world > 1 else None
+        if self._hyper_parameter_optimize_interval > 0 and self._counter % self._hyper_parameter_optimize_interval == 0:
+            self.optimize_hyperparameters(res["alpha_ss"])
+            ctx.set_alpha(self._alpha_alpha)
+        clock_m_step = time.time() - clock_m_step
+        joint_log_likelihood = res["doc_ll"] + topic_log_likelihood
+        print("e_step and m_step of iteration %d finished in %d and %d seconds respectively with log likelihood %g"
+              % (self._counter, clock_e_step, clock_m_step, joint_log_likelihood))
+        return joint_log_likelihood
+
     def learning(self):
         # :239-261
+        if self._resident_ok():
+            return self._learning_resident()
         self._counter += 1
         clock_e_step = time.time()
         document_log_likelihood, phi_sufficient_statistics = self.e_step()

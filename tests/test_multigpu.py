@@ -106,9 +106,9 @@ def test_launch_train_two_processes_matches_one(capfd):
         numpy.random.seed(100)
         launch_train.main(["--input_directory=%s" % os.path.join(tmp, "toy"), "--output_directory=%s" % os.path.join(tmp, "single"),
                            "--number_of_topics=6", "--training_iterations=3", "--snapshot_interval=3", "--inference_mode=2"])
-        single = [float(x) for x in re.findall(r"with log likelihood (\S+)", capfd.readouterr().out)]
+        single = [float(x) for x in re.findall(r"with log likelihood (-?[0-9.]+(?:e[+-]?[0-9]+)?)", capfd.readouterr().out)]
         mp.spawn(_train_rank, args=(2, tmp, 29631), nprocs=2, join=True)
-        multi = [float(x) for x in re.findall(r"with log likelihood (\S+)", capfd.readouterr().out)]
+        multi = [float(x) for x in re.findall(r"with log likelihood (-?[0-9.]+(?:e[+-]?[0-9]+)?)", capfd.readouterr().out)]
         run = os.listdir(os.path.join(tmp, "out", "toy"))
         assert len(run) == 1
         files = sorted(os.listdir(os.path.join(tmp, "out", "toy", run[0])))

@@ -38,11 +38,14 @@ def _vb_from_csr(row_ptr, ids, cts, K, V, eta, alpha, alpha_beta):
     return lda
 
 
-def test_learning_matches_reference_trace_config1():
-    """BASELINE.json configs[0]: associated-press, K=10, 20 VB iterations (E-step on the GPU, M-step and
-    alpha Newton update on the host exactly as the reference) against the reference's own ELBO trace
-    (BASELINE.md section 3)."""
+@pytest.mark.parametrize("resident", ["1", "0"])
+def test_learning_matches_reference_trace_config1(resident, monkeypatch):
+    """BASELINE.json configs[0]: associated-press, K=10, 20 VB iterations against the reference's own
+    ELBO trace.  resident=1: the model stays in HBM (device E-step + device
+    M-step + device alpha statistics, alpha Newton update on the host); resident=0: E-step on the GPU,
+    M-step on the host exactly as the reference."""
     from pylda_b200 import synthetic
+    monkeypatch.setenv("PYLDA_RESIDENT", resident)
     z = numpy.load(os.path.join(GOLDEN, "ap_full_k10_trace.npz"))
     K, V = int(z["K"]), int(z["V"])
     eta0 = synthetic.initial_eta(K, V, int(z["eta_seed"]))
@@ -61,6 +64,7 @@ def test_learning_matches_reference_trace_config1():
     assert max_rel(lda._alpha_alpha, z["final_alpha"]) <= RTOL
     assert max_rel(lda._gamma.sum(axis=1), z["final_gamma_rowsum"]) <= RTOL
     assert abs(lda._eta.sum() - (float(z["cts"].sum()) + K * V * float(z["alpha_beta"]))) <= 1e-6 * z["cts"].sum()
+    assert bool(lda.__dict__.get("_model_on_device")) == (resident == "1")
 
 
 def test_inference_heldout_and_gamma_untouched():
