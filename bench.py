@@ -285,14 +285,19 @@ def run_product(args):
         shell._alpha_alpha = alpha.copy()
         ctx.set_model(eta0, alpha)
         eta_host = None
+        em_wall = []
         for em in range(4):
+            t_em = time.perf_counter()
             ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
             alpha_ss = ctx.get_results(0, gamma=False, phi=False, alpha_ss=True)["alpha_ss"]
             _, eta_host = ctx.mstep_resident(alpha_beta, want_eta=(want_eta and em == 3))
             shell.optimize_hyperparameters(alpha_ss)
             ctx.set_alpha(shell._alpha_alpha)
+            em_wall.append(time.perf_counter() - t_em)
+        em_stats["ms"] = 1e3 * min(em_wall[:3])      # the 4th may include the eta copy-back
         return eta_host, shell._alpha_alpha.copy()
 
+    em_stats = {}
     results = {}
     sampler = ClockSampler(local_rank)
     alpha_warm = alpha
@@ -407,6 +412,9 @@ def run_product(args):
                     "mean_inner_trips": o["mean_trips"], "elbo_doc_ll": o["doc_ll"],
                     "roofline_frac": o["stats"]["algo_total_bytes"] / (o["ker_ms"] * 1e-3) / 1e9 / peak,
                     "roofline_frac_read": o["stats"]["algo_read_bytes"] / (o["ker_ms"] * 1e-3) / 1e9 / peak},
+            "em_iteration": {"what": "one whole resident EM iteration as VariationalBayes.learning() runs it: E-step + alpha "
+                                     "statistics + device M-step + host Newton update of alpha (wall clock, rank 0)",
+                             "ms": em_stats.get("ms")},
             "probe_1trip": {"what": "same corpus with local_parameter_iteration=1 (gather + one trip + scatter): the "
                                     "regime where the HBM roof binds", "kernel_ms": probe_ms,
                             "achieved": algo / (probe_ms * 1e-3) / 1e9, "unit": "GB/s",
