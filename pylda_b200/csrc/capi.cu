@@ -218,14 +218,14 @@ const void* lookup_v2(int LK, int J, int W, int V) {
     return nullptr;
 }
 
-const void* lookup_rt(int LK, int J, int W, int* R) {
+const void* lookup_rt(int LK, int J, int W, int Rsel, int NW, int* R) {
     switch (LK) {
-        case 1: return estep_rt_lk1(J, W, R);
-        case 2: return estep_rt_lk2(J, W, R);
-        case 4: return estep_rt_lk4(J, W, R);
-        case 8: return estep_rt_lk8(J, W, R);
-        case 16: return estep_rt_lk16(J, W, R);
-        case 32: return estep_rt_lk32(J, W, R);
+        case 1: return estep_rt_lk1(J, W, Rsel, NW, R);
+        case 2: return estep_rt_lk2(J, W, Rsel, NW, R);
+        case 4: return estep_rt_lk4(J, W, Rsel, NW, R);
+        case 8: return estep_rt_lk8(J, W, Rsel, NW, R);
+        case 16: return estep_rt_lk16(J, W, Rsel, NW, R);
+        case 32: return estep_rt_lk32(J, W, Rsel, NW, R);
     }
     return nullptr;
 }
@@ -419,9 +419,12 @@ int launch_estep_v1(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_
 // class has a row capacity and a document goes to the class with the smallest capacity that holds it.
 //   "WxG"  estep_v2: tile in shared memory, W warps per document, G documents in flight per CTA
 //          (W*G <= 8: 8-warp CTAs; 8 < W*G <= 16: the 16-warp variant);
-//   "rW"   estep_rt: tile in registers, W warps per document, 8/W documents in flight per CTA.
+//   "rW"   estep_rt: tile in registers, W warps per document, 8/W documents in flight per CTA;
+//   "rW/RxG[@LK:J]"  an explicitly compiled estep_rt variant with R rows per lane and G documents per CTA
+//          (12- and 16-warp CTAs; measured slower than the defaults -- multi-warp groups pay barriers and
+//          duplicated owner phases -- kept as a tuning aid).
 // PYLDA_CLASSES overrides the default list (tuning aid).
-struct ClassCfg { int kind, W, G; };
+struct ClassCfg { int kind, W, G, R, LK, J; };
 
 std::vector<ClassCfg> class_config() {
     std::vector<ClassCfg> out;
@@ -432,16 +435,20 @@ std::vector<ClassCfg> class_config() {
         size_t end = spec.find(',', pos);
         if (end == std::string::npos) end = spec.size();
         const std::string item = spec.substr(pos, end - pos);
-        int W = 0, G = 0;
-        if (sscanf(item.c_str(), "r%d", &W) == 1) {
-            if (W == 1 || W == 2 || W == 4 || W == 8) out.push_back({1, W, 8 / W});
+        int W = 0, G = 0, R = 0, LK = 0, J = 0;
+        const int nf = sscanf(item.c_str(), "r%d/%dx%d@%d:%d", &W, &R, &G, &LK, &J);
+        if (nf >= 3) {                    // explicit register-tile variant "rW/RxG[@LK:J]" (must be compiled)
+            if (nf != 5) LK = J = 0;
+            if ((W == 1 || W == 2 || W == 4 || W == 8) && R >= 1 && G >= 1 && W * G <= 16) out.push_back({1, W, G, R, LK, J});
+        } else if (sscanf(item.c_str(), "r%d", &W) == 1) {
+            if (W == 1 || W == 2 || W == 4 || W == 8) out.push_back({1, W, 8 / W, 0, 0, 0});
         } else if (sscanf(item.c_str(), "%dx%d", &W, &G) == 2 &&
                    (W == 1 || W == 2 || W == 4 || W == 8) && G >= 1 && W * G <= (W > 1 ? 16 : 8)) {
-            out.push_back({0, W, G});
+            out.push_back({0, W, G, 0, 0, 0});
         }
         pos = end + 1;
     }
-    if (out.empty()) out = {{0, 8, 1}};
+    if (out.empty()) out = {{0, 8, 1, 0, 0, 0}};
     return out;
 }
 
@@ -562,8 +569,12 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     struct Cls { int kind, W, G, cap, LK, J; const void* fn; long long lo, hi; };
     std::vector<Cls> cls;
     for (const ClassCfg& c : class_config()) {
-        int lk = 0, j = 0;
-        if (!pick_shape(K, &lk, &j, true, c.W)) continue;
+        int lk = c.LK, j = c.J;
+        if (lk > 0) {
+            if (lk * j < (K + 1) / 2) continue;            // forced shape too narrow for K
+        } else if (!pick_shape(K, &lk, &j, true, c.W)) {
+            continue;
+        }
         const int kpad = 2 * lk * j, ln = 32 / lk;
         if (kpad > 128 * c.W) continue;                    // at most 4 topics per owner thread
         if (c.kind == 0) {
@@ -575,7 +586,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             if (n > 0 && fn) cls.push_back({0, c.W, c.G, n, lk, j, fn, 0, 0});
         } else if (use_rt) {
             int R = 0;
-            const void* fn = lookup_rt(lk, j, c.W, &R);
+            const void* fn = lookup_rt(lk, j, c.W, c.R, c.R ? c.W * c.G : 0, &R);
             if (!fn) continue;
             const int cap = c.W * ln * R;
             const GroupLayout gl = group_layout_rt(c.W, lk, kpad, cap, ST);
@@ -690,6 +701,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             nmax = c.cap;
             gl = group_layout_rt(W, c.LK, kpad, c.cap, ST);
             G = c.G;
+            if (const char* e = getenv("PYLDA_RT_G")) G = std::max(1, std::min(G, atoi(e)));   // tuning aid
         } else {
             nmax = std::max(ln, (ns[c.lo] + ln - 1) / ln * ln);
             gl = group_layout_v2(W, c.LK, kpad, nmax, ST);

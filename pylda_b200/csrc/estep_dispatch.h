@@ -14,13 +14,14 @@ const void* estep_v2_lk4(int J, int W, int V);
 const void* estep_v2_lk8(int J, int W, int V);
 const void* estep_v2_lk16(int J, int W, int V);
 const void* estep_v2_lk32(int J, int W, int V);
-// register-tile generation (estep_rt.cuh); *rows_per_lane = R, a group holds W * (32/LK) * R rows
-const void* estep_rt_lk1(int J, int W, int* rows_per_lane);
-const void* estep_rt_lk2(int J, int W, int* rows_per_lane);
-const void* estep_rt_lk4(int J, int W, int* rows_per_lane);
-const void* estep_rt_lk8(int J, int W, int* rows_per_lane);
-const void* estep_rt_lk16(int J, int W, int* rows_per_lane);
-const void* estep_rt_lk32(int J, int W, int* rows_per_lane);
+// register-tile generation (estep_rt.cuh); a group holds W * (32/LK) * R rows.  R = NWARPS = 0: the default
+// variant (its R is returned in *rows_per_lane); otherwise an explicitly compiled (R, warps per CTA) variant
+const void* estep_rt_lk1(int J, int W, int R, int NWARPS, int* rows_per_lane);
+const void* estep_rt_lk2(int J, int W, int R, int NWARPS, int* rows_per_lane);
+const void* estep_rt_lk4(int J, int W, int R, int NWARPS, int* rows_per_lane);
+const void* estep_rt_lk8(int J, int W, int R, int NWARPS, int* rows_per_lane);
+const void* estep_rt_lk16(int J, int W, int R, int NWARPS, int* rows_per_lane);
+const void* estep_rt_lk32(int J, int W, int R, int NWARPS, int* rows_per_lane);
 // cluster generation (estep_cl.cuh): one long document per thread-block cluster of 2, 4 or 8 CTAs
 const void* estep_cl_lookup(int LK, int J);
 // second-generation streaming kernel (documents longer than every resident class)

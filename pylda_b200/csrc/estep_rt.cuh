@@ -24,10 +24,10 @@ struct RtRows {
     static constexpr int R = (J <= 5) ? 8 : (J <= 7) ? 6 : (J <= 8) ? 5 : (J <= 13) ? 3 : 2;
 };
 
-template <int LK, int J, int W>
+template <int LK, int J, int W, int RR_>
 struct RtCfg {
     static constexpr int LN = 32 / LK;
-    static constexpr int R = RtRows<J>::R;
+    static constexpr int R = RR_;
     static constexpr int KPAD = 2 * LK * J;
     static constexpr int GT = 32 * W;
     static constexpr int U = (KPAD + GT - 1) / GT;
@@ -41,11 +41,11 @@ struct RtCfg {
 
 // Everything between "tile is in shared memory" and "phi rows are in shared memory" for a warp
 // that holds RU row groups (RU * LN rows) of the document in registers.
-template <int LK, int J, int W, int RU>
+template <int LK, int J, int W, int RMAX, int RU>
 __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* spart, double* red, const double* cnt,
                                         const double* mwr, double* tile, int n, int g, int gt, int gw, int lane,
                                         bool warp_owns, const double* als, double* gams, double& lacc_out) {
-    using C = RtCfg<LK, J, W>;
+    using C = RtCfg<LK, J, W, RMAX>;
     constexpr int LN = C::LN, R = C::R, KPAD = C::KPAD, GT = C::GT, U = C::U, NB = C::NB, NP = C::NP;
     constexpr int RA = RU > 0 ? RU : 1;
     const int kl = lane % LK, nl = lane / LK;
@@ -210,9 +210,13 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
     return it;
 }
 
-template <int LK, int J, int W>
-__global__ void __launch_bounds__(256) estep_rt(const EParams p) {
-    using C = RtCfg<LK, J, W>;
+// RMAX = rows a lane keeps in registers, NWARPS = warps per CTA (register budget 65536 / (32 NWARPS)):
+// the default (RtRows<J>::R, 8 warps, 255 registers) holds the most rows per warp; smaller RMAX with 12 or
+// 16 warps per CTA trades rows per warp for warps per scheduler (a lone warp needs ~2700 cycles per trip
+// for ~850 cycles of fp64 pipe: the kernels are latency bound, so more resident warps is more throughput).
+template <int LK, int J, int W, int RMAX, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) estep_rt(const EParams p) {
+    using C = RtCfg<LK, J, W, RMAX>;
     constexpr int LN = C::LN, R = C::R, KPAD = C::KPAD, GT = C::GT, U = C::U, CAP = C::CAP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) estep_rt(const EParams p) {
 #define PYLDA_RT_CASE(X)                                                                                     \
     case X:                                                                                                  \
         if constexpr (X <= R)                                                                                \
-            it = rt_trips<LK, J, W, X>(p, es2, spart, red, cnt, mwr, tile, n, g, gt, gw, lane, warp_owns, als, \
+            it = rt_trips<LK, J, W, RMAX, X>(p, es2, spart, red, cnt, mwr, tile, n, g, gt, gw, lane, warp_owns, als, \
                                        gams, lacc);                                                          \
         break;
         switch (RU) {

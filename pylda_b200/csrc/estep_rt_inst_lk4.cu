@@ -1,20 +1,30 @@
 // Instantiations of the register-tile per-document E-step kernel for LK = 4 topic-lanes per row.
-// Only shapes with at most 4 topics per owner thread (2*LK*J <= 128*W) exist.
+// Only shapes with at most 4 topics per owner thread (2*LK*J <= 128*W) exist.  R = 0 / NWARPS = 0 select
+// the default variant (RtRows<J>::R rows per lane, 8 warps per CTA); *rows_per_lane returns its R.
 #include "estep_rt.cuh"
 #include "estep_dispatch.h"
 namespace pylda {
-const void* estep_rt_lk4(int J, int W, int* rows_per_lane) {
+const void* estep_rt_lk4(int J, int W, int R, int NWARPS, int* rows_per_lane) {
     constexpr int LK = 4;
 #define PYLDA_CASE_W(JJ, WW) \
-    if constexpr (2 * LK * JJ <= 128 * WW) { if (J == JJ && W == WW) { *rows_per_lane = RtRows<JJ>::R; return (const void*)estep_rt<LK, JJ, WW>; } }
+    if constexpr (2 * LK * JJ <= 128 * WW) {                                                                   \
+        if (J == JJ && W == WW && R == 0) {                                                                    \
+            *rows_per_lane = RtRows<JJ>::R;                                                                    \
+            return (const void*)estep_rt<LK, JJ, WW, RtRows<JJ>::R, 8>;                                        \
+        }                                                                                                      \
+    }
 #define PYLDA_CASE(JJ) PYLDA_CASE_W(JJ, 1) PYLDA_CASE_W(JJ, 2) PYLDA_CASE_W(JJ, 4) PYLDA_CASE_W(JJ, 8)
     PYLDA_CASE(5)
     PYLDA_CASE(7)
     PYLDA_CASE(8)
     PYLDA_CASE(13)
-
 #undef PYLDA_CASE
 #undef PYLDA_CASE_W
+    *rows_per_lane = R;
+    // more warps per SM with fewer rows per lane (K ~ 100 shapes; tuning set)
+#define PYLDA_ALT(JJ, WW, RR, NW) if (J == JJ && W == WW && R == RR && NWARPS == NW) return (const void*)estep_rt<LK, JJ, WW, RR, NW>;
+    PYLDA_ALT(13, 2, 2, 10) PYLDA_ALT(13, 1, 2, 10) PYLDA_ALT(13, 2, 1, 16) PYLDA_ALT(13, 4, 1, 16) PYLDA_ALT(13, 4, 2, 12)
+#undef PYLDA_ALT
     return nullptr;
 }
 }  // namespace pylda
