@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) estep_cl(const EParams p) {
                 const int r = r0 + nl;
                 const bool ok = r < nloc;
                 double b[2 * J];
-                const double part = row_dot<LK, J>(rowp, e, b);
+                const double part = row_dot<LK, J>(rowp, e, b, ok ? min(J, (KP2 - kl + LK - 1) / LK) : 0);
                 const double c = cnt[r];
                 const double w = ok ? c * rcp_nr(part) : 0.0;
                 if (ok && kl == 0) lacc = fma(c, mwr[r] + log(part), lacc);

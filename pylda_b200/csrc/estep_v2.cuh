@@ -30,11 +30,17 @@ __device__ __forceinline__ void gsync(int g) {
     }
 }
 
+// npairs: pairs of this lane that lie inside the row (kl + LK*j < KP/2).  The trip loops pass J (no
+// predicate: the over-read of the next row is multiplied by e = 0 and nobody writes the tile then); the
+// final passes, which overwrite tile rows with phi while other warps still read their own rows, pass the
+// true count so that no lane ever reads a row it does not own (compute-sanitizer racecheck clean).
 template <int LK, int J>
-__device__ __forceinline__ double row_dot(const double* rowp, const double (&e)[2 * J], double (&b)[2 * J]) {
+__device__ __forceinline__ double row_dot(const double* rowp, const double (&e)[2 * J], double (&b)[2 * J],
+                                          int npairs = J) {
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(rowp + 2 * LK * j);
+        double2 v = make_double2(0.0, 0.0);
+        if (j < npairs) v = *reinterpret_cast<const double2*>(rowp + 2 * LK * j);
         b[2 * j] = v.x;
         b[2 * j + 1] = v.y;
     }
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) 
                 const int r = r0 + nl;
                 const bool ok = r < n;
                 double b[2 * J];
-                const double part = row_dot<LK, J>(rowp, e, b);
+                const double part = row_dot<LK, J>(rowp, e, b, ok ? min(J, (KP2 - kl + LK - 1) / LK) : 0);
                 const double c = cnt[r];
                 const double w = ok ? c * rcp_nr(part) : 0.0;
                 if (ok && kl == 0) lacc = fma(c, mwr[r] + log(part), lacc);   // sum_n c_n logsumexp_n
