@@ -5,25 +5,26 @@ cat > /tmp/san.py <<'PY'
 import os, sys, numpy
 sys.path.insert(0, os.getcwd())
 from pylda_b200 import native, synthetic
-K, V = 100, 3000
+V = 3000
 a = synthetic.synthetic_corpus(60, V, seed=99, length="zipf")
 b = synthetic.synthetic_corpus(2, V, seed=98, length="poisson", mean_len=3000)
 row_ptr = numpy.concatenate([a[0], a[0][-1] + b[0][1:]])
 ids, cts = numpy.concatenate([a[1], b[1]]), numpy.concatenate([a[2], b[2]])
-eta = synthetic.initial_eta(K, V, 1)
-alpha = numpy.full(K, 1.0 / K)
 ctx = native.EStepContext(0)
 ctx.set_corpus(0, row_ptr, ids, cts)
-for kern in ("default", "v2", "cluster", "v1"):
-    if kern == "default":
-        os.environ.pop("PYLDA_KERNEL", None)
-    else:
-        os.environ["PYLDA_KERNEL"] = kern
-    out = ctx.estep(0, eta, alpha, 6, 1e-6, heldout=True, want_alpha_ss=True)
-    print(kern, out["doc_ll"], out["stats"]["n_estep_launches"], flush=True)
+for K in (100, 10, 50, 200, 500):
+    eta = synthetic.initial_eta(K, V, 1)
+    alpha = numpy.full(K, 1.0 / K)
+    for kern in ("default", "v2", "cluster", "v1"):
+        if kern == "default":
+            os.environ.pop("PYLDA_KERNEL", None)
+        else:
+            os.environ["PYLDA_KERNEL"] = kern
+        out = ctx.estep(0, eta, alpha, 4, 1e-6, heldout=True, want_alpha_ss=True)
+        print("K=%d" % K, kern, out["doc_ll"], out["stats"]["n_estep_launches"], flush=True)
 ctx.close()
 PY
 for tool in memcheck racecheck; do
   echo "=== $tool" | tee -a gpurun_out/sanitize.log
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py 2>&1 | grep -v "^=========     at\|^=========     by\|^=========         in" | tail -25 | tee -a gpurun_out/sanitize.log
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py 2>&1 | grep -v "^=========     at\|^=========     by\|^=========         in" | tail -40 | tee -a gpurun_out/sanitize.log
 done
