@@ -598,7 +598,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     // equal capacities: keep the first
     cls.erase(std::unique(cls.begin(), cls.end(), [](const Cls& a, const Cls& b) { return a.cap == b.cap; }), cls.end());
     const int NC = (int)cls.size();
-    if (NC > 13) return fail(ctx, "too many length classes");
+    if (NC > 12) return fail(ctx, "too many length classes");
 
     const std::vector<int>& ns = cp.n_sorted;
     const long long D = cp.D;
@@ -726,6 +726,11 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
         p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
         p.W = W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = G * gl.bytes;
+        {
+            const char* ce = getenv("PYLDA_COMPACT");
+            p.compact = !(ce && !strcmp(ce, "0"));
+            p.revived = ctx->counters + 14;
+        }
         p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
         p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
         void* args[] = {&p};
@@ -1015,6 +1020,11 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     st.inner_iters = (int64_t)llround(ctx->last_scal[3]);
     st.docs_at_cap = (int64_t)llround(ctx->last_scal[4]);
     st.row_trips = ctx->last_scal[5];
+    {
+        int rv = 0;
+        cudaMemcpy(&rv, ctx->counters + 14, sizeof(int), cudaMemcpyDeviceToHost);
+        st.revived_docs = rv;
+    }
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;
     st.algo_total_bytes = st.algo_read_bytes + 8.0 * (double)cp.D * K + 8.0 * (double)cp.nnz * K;
     if (stats) *stats = st;

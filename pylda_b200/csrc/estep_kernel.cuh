@@ -55,6 +55,8 @@ struct EParams {
     // group geometry
     int W;                           // warps per group
     int nmax;                        // tile capacity in rows (RES only)
+    int compact;                     // estep_rt: dead-topic elimination enabled
+    int* revived;                    // estep_rt: counter of documents in which an eliminated topic came back
     int group_bytes;                 // bytes of shared memory per group
     int off_groups;                  // byte offset of group 0 (after the CTA-wide alpha copy)
     int off_gam, off_spart, off_red, off_cnt, off_mwr, off_rid, off_tile;   // within a group

@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -34,6 +34,7 @@ class Stats(ctypes.Structure):
         ("docs_resident", ctypes.c_int64),
         ("docs_streamed", ctypes.c_int64),
         ("row_trips", ctypes.c_double),
+        ("revived_docs", ctypes.c_int64),
     ]
 
     def as_dict(self):
