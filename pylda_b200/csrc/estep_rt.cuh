@@ -69,13 +69,13 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
         }
     }
 
-    // Dead-topic elimination (single-warp groups).  Once gamma_k == alpha_k bit for bit, topic k adds less
+    // Dead-topic elimination.  Once gamma_k == alpha_k bit for bit, topic k adds less
     // than half an ulp to every norm and to its own gamma (that IS the condition), e_k stops changing and
     // the topic never comes back (measured: 78 % of the topics by trip 10, 90 % by trip 20 at the headline
     // config, no revival in any corpus tried; a revival is detected in the final pass and counted).  When
     // at most 32 topics are still alive the trips continue on a compact 32-column copy of the tile:
     // 4*R*CJ instead of 4*R*J DFMA per lane and one exp(psi) pass instead of U.
-    constexpr bool COMPACT = (W == 1) && (LK >= 4) && (LK <= 16) && (KPAD > 32);
+    constexpr bool COMPACT = (LK >= 4) && (LK <= 16) && (KPAD > 32) && (W * LN * 32 + 48 <= NP * KPAD);
     constexpr int CJ = COMPACT ? 16 / LK : 1;           // compact topic pairs per lane (32 columns)
     bool go_compact = false;
     int nlive = 0;
@@ -192,12 +192,21 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
             }
         }
         dsum = warp_sum(dsum);
+        int slot0 = 0;                                                   // first compact slot of this warp
         if (W > 1) {
-            if (lane == 0) red[gw] = dsum;
+            if (lane == 0) {
+                red[gw] = dsum;
+                red[W + gw] = (double)nlive;
+            }
             gsync<W>(g);
             dsum = 0.0;
+            nlive = 0;
 #pragma unroll
-            for (int x = 0; x < W; ++x) dsum += red[x];
+            for (int x = 0; x < W; ++x) {
+                dsum += red[x];
+                if (x < gw) slot0 += (int)red[W + x];
+                nlive += (int)red[W + x];
+            }
         } else {
             __syncwarp();
         }
@@ -206,9 +215,10 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
             // ---- switch: both e buffers get the current e of every topic (dead ones keep it for good),
             // the live topics are numbered 0 .. nlive-1 in topic order
             double* eso = es2 + ((it + 1) & 1) * KPAD;
-            int* livecol = reinterpret_cast<int*>(spart + LN * 32);
-            double* es_c = spart + LN * 32 + 16;
-            int base_slot = 0;
+            // (the column partials in spart have been consumed: every warp is past the second barrier)
+            int* livecol = reinterpret_cast<int*>(spart + W * LN * 32);
+            double* es_c = spart + W * LN * 32 + 16;
+            int base_slot = slot0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = gt + GT * u;
@@ -220,20 +230,20 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                 }
                 base_slot += __popc(alive[u]);
             }
-            if (lane >= nlive) {
+            if (gw == 0 && lane >= nlive) {
                 livecol[lane] = 0;
                 es_c[lane] = 0.0;
             }
-            __syncwarp();
+            gsync<W>(g);
             go_compact = true;
             break;
         }
     }
 
     if (COMPACT && go_compact) {
-        int* livecol = reinterpret_cast<int*>(spart + LN * 32);
-        double* es_c = spart + LN * 32 + 16;
-        double* spart_c = spart;                                          // [LN][32]
+        int* livecol = reinterpret_cast<int*>(spart + W * LN * 32);
+        double* es_c = spart + W * LN * 32 + 16;
+        double* spart_c = spart;                                          // [W * LN][32]
         // the lane's compact tile: RU rows x 2*CJ live columns, gathered from the staged tile
         double bc[RA][2 * CJ];
 #pragma unroll
@@ -247,8 +257,8 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                 bc[i][2 * jj + 1] = rowp[c1];
             }
         }
-        // lane t owns live slot t
-        const bool valid = lane < nlive;
+        // lane t of the group's first warp owns live slot t
+        const bool valid = (gw == 0) && lane < nlive;
         const int kt = livecol[lane];
         const double alt = als[kt];
         double gcur = gams[kt];
@@ -283,32 +293,42 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                     s0 = fma(w[i], bc[i][2 * jj], s0);
                     s1 = fma(w[i], bc[i][2 * jj + 1], s1);
                 }
-                *reinterpret_cast<double2*>(spart_c + nl * 32 + 2 * (kl + LK * jj)) = make_double2(s0, s1);
+                *reinterpret_cast<double2*>(spart_c + (gw * LN + nl) * 32 + 2 * (kl + LK * jj)) = make_double2(s0, s1);
             }
-            __syncwarp();
-            double ss0 = 0.0, ss1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < LN; q += 2) {
-                ss0 += spart_c[q * 32 + lane];
-                if (q + 1 < LN) ss1 += spart_c[(q + 1) * 32 + lane];
-            }
-            const double gnc = fma(et, ss0 + ss1, alt);                   // :185
-            double dsum = valid ? fabs(gnc - gcur) : 0.0;                 // :187 (dead topics contribute exactly 0)
-            if (valid) gcur = gnc;                                        // :188
-            const double enc = exp_digamma(valid ? gnc : 1.0);
+            gsync<W>(g);
             ++it;
-            dsum = warp_sum(dsum);
-            if (dsum <= tolK || it >= p.max_iter) break;                  // :189-190 / :174
-            et = enc;
-            es_c[lane] = valid ? enc : 0.0;
-            __syncwarp();
+            bool done = false;
+            if (gw == 0) {
+                double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
+#pragma unroll
+                for (int q = 0; q < W * LN; q += 4) {
+                    ss0 += spart_c[q * 32 + lane];
+                    if (q + 1 < W * LN) ss1 += spart_c[(q + 1) * 32 + lane];
+                    if (q + 2 < W * LN) ss2 += spart_c[(q + 2) * 32 + lane];
+                    if (q + 3 < W * LN) ss3 += spart_c[(q + 3) * 32 + lane];
+                }
+                const double gnc = fma(et, (ss0 + ss1) + (ss2 + ss3), alt);   // :185
+                double dsum = valid ? fabs(gnc - gcur) : 0.0;             // :187 (dead topics contribute exactly 0)
+                if (valid) gcur = gnc;                                    // :188
+                const double enc = exp_digamma(valid ? gnc : 1.0);
+                dsum = warp_sum(dsum);
+                done = dsum <= tolK || it >= p.max_iter;                  // :189-190 / :174
+                if (!done) {
+                    et = enc;
+                    es_c[lane] = valid ? enc : 0.0;
+                }
+                if (W > 1 && lane == 0) red[0] = done ? 1.0 : 0.0;
+            }
+            gsync<W>(g);
+            if (W > 1) done = red[0] != 0.0;
+            if (done) break;
         }
         // back to the full-width arrays: gamma, and the e of the LAST trip into the buffer the final pass reads
         if (valid) {
             gams[kt] = gcur;
             es2[((it - 1) & 1) * KPAD + kt] = et;
         }
-        __syncwarp();
+        gsync<W>(g);
     }
 
     // ---- phi from the LAST e (buffer (it-1)&1; w[] and part[] are those of the last trip) -------
@@ -334,9 +354,15 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                 s0 = fma(w[i], bv.x, s0);
                 s1 = fma(w[i], bv.y, s1);
             }
-            *reinterpret_cast<double2*>(spart + nl * KPAD + 2 * (kl + LK * j)) = make_double2(s0, s1);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 16 >> q);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16 >> q);
+            }
+            if (NB == 0 || nl < (LN >> NB))
+                *reinterpret_cast<double2*>(spart + (gw * (LN >> NB) + nl) * KPAD + 2 * (kl + LK * j)) = make_double2(s0, s1);
         }
-        __syncwarp();
+        gsync<W>(g);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int k = gt + GT * u;
@@ -347,7 +373,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                 came_back |= fma(es[k], ss, als[k]) != als[k];
             }
         }
-        if (__any_sync(0xffffffffu, came_back) && lane == 0 && p.revived) atomicAdd(p.revived, 1);
+        if (came_back && p.revived) atomicAdd(p.revived, 1);
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
