@@ -13,6 +13,8 @@ def _check(out, ref_gamma, ref_phi, ref_doc_ll, tag):
     ep = max_rel(out["phi_ss"], ref_phi, floor=PHI_FLOOR)
     el = abs(out["doc_ll"] - ref_doc_ll) / abs(ref_doc_ll)
     print("%s: gamma %.2e phi_ss %.2e doc_ll %.2e" % (tag, eg, ep, el))
+    if out.get("stats"):
+        assert out["stats"]["revived_docs"] == 0, (tag, "a topic eliminated as dead came back")
     assert eg <= RTOL, (tag, "gamma", eg)
     assert ep <= RTOL, (tag, "phi_ss", ep)
     assert el <= RTOL, (tag, "doc_ll", el)
@@ -293,3 +295,27 @@ def test_pathologically_long_document(ctx):
     _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "long document")
     assert out["stats"]["docs_streamed"] >= 1
     assert out["stats"]["n_estep_launches"] >= 2
+
+
+def test_dead_topic_elimination_changes_nothing(ctx, monkeypatch):
+    """PYLDA_COMPACT=0 (every trip at full width) and the default (topics with gamma_k == alpha_k dropped,
+    trips continued on a 32-column compact tile) must agree to rounding, with identical trip counts and
+    no revival; short, medium and long documents, symmetric alpha small enough for topics to die."""
+    from pylda_b200 import synthetic
+    K, V = 100, 20000
+    row_ptr, ids, cts = synthetic.synthetic_corpus(3000, V, seed=41, length="zipf")
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    monkeypatch.setenv("PYLDA_COMPACT", "0")
+    full = ctx.estep(0, eta, alpha, 50, 1e-6)
+    it_full = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    monkeypatch.delenv("PYLDA_COMPACT")
+    fast = ctx.estep(0, eta, alpha, 50, 1e-6)
+    it_fast = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    assert fast["stats"]["revived_docs"] == 0
+    assert numpy.array_equal(it_full, it_fast)
+    assert max_rel(fast["gamma"], full["gamma"]) <= 1e-12
+    assert max_rel(fast["phi_ss"], full["phi_ss"], floor=PHI_FLOOR) <= 1e-10
+    assert abs(fast["doc_ll"] - full["doc_ll"]) <= 1e-12 * abs(full["doc_ll"])
+    assert fast["stats"]["kernel_ms"] < full["stats"]["kernel_ms"]

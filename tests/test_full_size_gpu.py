@@ -34,6 +34,7 @@ def _properties_and_subsample(ctx, D, V, K, length, seed, n_sample, mean_len=100
     assert numpy.allclose(phi.sum(axis=0), cf, rtol=1e-9, atol=1e-9)
     assert res["iters"].min() >= 1 and res["iters"].max() <= 50
     assert numpy.isfinite(out["doc_ll"]) and out["stats"]["inner_iters"] == int(res["iters"].sum())
+    assert out["stats"]["revived_docs"] == 0          # dead-topic elimination never dropped a topic that mattered
     # alpha statistics from the device == the reference's host formula on the returned gamma (:232-233)
     import scipy.special as sp
     blk = slice(0, min(D, 50000))
