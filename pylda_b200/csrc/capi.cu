@@ -289,7 +289,7 @@ GroupLayout group_layout_rt(int W, int LK, int KPAD, int cap, int ST) {
     o += 2 * KPAD * 8;                // e, double buffered
     g.off_gam = 0;
     g.off_spart = o; o += NP * KPAD * 8;
-    g.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    g.off_red = o;   o += align_up(4 * W + 2, 2) * 8;   // dsum [W], ELBO pairs [2W], live counts [W]
     g.off_cnt = o;   o += cap * 8;
     g.off_mwr = o;   o += cap * 8;
     g.off_rid = o;   o += cap * 4;
@@ -306,7 +306,7 @@ GroupLayout group_layout_cl(int KPAD, int cap, int ST) {
     int o = 16;
     o += KPAD * 8;                    // es
     g.off_spart = o; o += W * KPAD * 8;
-    g.off_red = o;   o += align_up(3 * W + 2, 2) * 8;
+    g.off_red = o;   o += align_up(4 * W + 2, 2) * 8;   // dsum [W], ELBO pairs [2W], live counts [W]
     g.off_gam = o;   o += 2 * 8 * KPAD * 8;   // exchange slots [2][8][KPAD]
     g.off_cnt = o;   o += cap * 8;
     g.off_mwr = o;   o += cap * 8;

@@ -196,7 +196,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
         if (W > 1) {
             if (lane == 0) {
                 red[gw] = dsum;
-                red[W + gw] = (double)nlive;
+                red[3 * W + gw] = (double)nlive;      // (red[W .. 3W) belongs to the ELBO exchange at the end)
             }
             gsync<W>(g);
             dsum = 0.0;
@@ -204,8 +204,8 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
 #pragma unroll
             for (int x = 0; x < W; ++x) {
                 dsum += red[x];
-                if (x < gw) slot0 += (int)red[W + x];
-                nlive += (int)red[W + x];
+                if (x < gw) slot0 += (int)red[3 * W + x];
+                nlive += (int)red[3 * W + x];
             }
         } else {
             __syncwarp();

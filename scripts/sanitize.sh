@@ -20,7 +20,7 @@ for K in (100, 10, 50, 200, 500):
             os.environ.pop("PYLDA_KERNEL", None)
         else:
             os.environ["PYLDA_KERNEL"] = kern
-        out = ctx.estep(0, eta, alpha, 4, 1e-6, heldout=True, want_alpha_ss=True)
+        out = ctx.estep(0, eta, alpha, 12, 1e-6, heldout=True, want_alpha_ss=True)
         print("K=%d" % K, kern, out["doc_ll"], out["stats"]["n_estep_launches"], flush=True)
 ctx.close()
 PY
