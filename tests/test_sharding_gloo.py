@@ -6,7 +6,6 @@ import os
 import tempfile
 
 import numpy
-import pytest
 
 
 def test_shard_bounds_cover_and_balance():
