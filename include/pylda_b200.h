@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 6
+#define PYLDA_ABI_VERSION 7
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -56,6 +56,8 @@ typedef struct pylda_stats {
     double  row_trips;         /* sum_d n_d * iters_d: 4*KP*row_trips = fp64 flops of the mat-vecs */
     int64_t revived_docs;      /* documents in which a topic eliminated as dead (gamma_k == alpha_k) would have
                                   come back; must be 0 (then the elimination changed nothing), local to the rank */
+    int64_t docs_narrow_wide;     /* documents handed to the 16-column narrow stage (at most 16 topics alive)     */
+    int64_t docs_narrow;      /* documents that went through the 8-column narrow stage (at most 8 alive)      */
 } pylda_stats;
 
 /* ABI version of the loaded library (== PYLDA_ABI_VERSION of the header it was built from). */

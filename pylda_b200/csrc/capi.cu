@@ -16,6 +16,7 @@
 #include "../../include/pylda_b200.h"
 #include "estep_dispatch.h"
 #include "estep_kernel.cuh"
+#include "estep_narrow.cuh"
 #include "prep_kernels.cuh"
 
 using namespace pylda;
@@ -88,6 +89,10 @@ struct Corpus {
     int* iters = nullptr;
     bool has_results = false;
     int results_K = 0;
+    // hand-over buffers of the narrow stages (estep_narrow.cuh)
+    int* park_rec = nullptr;         // PARK_REC ints per document
+    double* park_gam = nullptr;      // PARK_GAM doubles per document
+    int* park_lists = nullptr;       // PARK_LISTS lists of D documents
 };
 
 }  // namespace
@@ -103,7 +108,7 @@ struct pylda_ctx {
     int K = 0, V = 0, KP = 0;
     double* eta = nullptr;       // (K, V)
     double* alpha = nullptr;     // (K,)
-    double alpha_max = 0.0, alpha_term = 0.0;
+    double alpha_max = 0.0, alpha_min = 0.0, alpha_sum = 0.0, lg_alpha = 0.0, alpha_term = 0.0;
     std::vector<double> alpha_host;
     double* Elt = nullptr;       // (V, KP) E_log_eta transposed
     double* Bt = nullptr;        // (V, KP)
@@ -116,6 +121,8 @@ struct pylda_ctx {
     double* partial = nullptr;   // reduction scratch
     size_t partial_cap = 0;
     int* counters = nullptr;     // class queue heads
+    int* park_ctr = nullptr;     // narrow stages: list lengths [0..8) and queue heads [8..16)
+    double* e_dead = nullptr;    // (K,) exp(psi(alpha_k))
     bool model_set = false;
     bool phi_KV_valid = false;
     bool have_alpha_ss = false;
@@ -155,13 +162,14 @@ cudaError_t dalloc(T** p, size_t n) {
 void free_corpus(Corpus& c) {
     cudaFree(c.row_ptr); cudaFree(c.ids); cudaFree(c.cts); cudaFree(c.order);
     cudaFree(c.gamma); cudaFree(c.docterm); cudaFree(c.iters);
+    cudaFree(c.park_rec); cudaFree(c.park_gam); cudaFree(c.park_lists);
     c = Corpus();
 }
 
 void free_model(pylda_ctx* c) {
     cudaFree(c->eta); cudaFree(c->alpha); cudaFree(c->Elt); cudaFree(c->Bt); cudaFree(c->mw);
-    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss);
-    c->eta = c->alpha = c->Elt = c->Bt = c->mw = c->phi = c->phi_KV = c->kbuf = c->alpha_ss = nullptr;
+    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss); cudaFree(c->e_dead);
+    c->eta = c->alpha = c->Elt = c->Bt = c->mw = c->phi = c->phi_KV = c->kbuf = c->alpha_ss = c->e_dead = nullptr;
     c->model_set = false;
 }
 
@@ -550,6 +558,73 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     return 0;
 }
 
+// psi(x), x > 0, on the host (recurrence + asymptotic series; ~1e-13): only feeds the safety bound below
+double host_digamma(double x) {
+    double r = 0.0;
+    while (x < 8.0) { r -= 1.0 / x; x += 1.0; }
+    const double u = 1.0 / (x * x);
+    return r + log(x) - 0.5 / x - u * (1.0 / 12 - u * (1.0 / 120 - u * (1.0 / 252 - u * (1.0 / 240 - u * (1.0 / 132)))));
+}
+
+// Narrow stages (estep_narrow.cuh): configuration of one E-step.  A topic eliminated as dead stays dead while
+// e_k s_k < ulp(alpha_k)/2, s_k <= sum_n w_n; chk_bound = alpha_min 2^-54 / exp(psi(alpha_max)) is the value
+// of sum_n w_n below which that is certain.  The hand-over is only used when the bound leaves three orders
+// of magnitude of room (alpha <~ 0.02); the kernels check every document against it.
+struct ParkCfg { int nc; int exact_phi; double chk_bound; };
+ParkCfg park_config(const pylda_ctx* ctx) {
+    ParkCfg c;
+    const char* e = getenv("PYLDA_PARK");
+    c.nc = 16;
+    if (e && *e) c.nc = atoi(e);
+    if (c.nc != 8 && c.nc != 16) c.nc = 0;
+    const char* x = getenv("PYLDA_EXACT_PHI");
+    c.exact_phi = (x && !strcmp(x, "1")) ? 1 : 0;
+    const double ed = exp(host_digamma(ctx->alpha_max));
+    c.chk_bound = ed > 0.0 ? ctx->alpha_min * ldexp(1.0, -54) / ed : HUGE_VAL;
+    if (!(c.chk_bound >= 1e3)) c.nc = 0;
+    const char* ce = getenv("PYLDA_COMPACT");
+    if (ce && !strcmp(ce, "0")) c.nc = 0;
+    return c;
+}
+
+int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, double tol, pylda_stats* st, ClassTimer& timer) {
+    k_e_dead<<<(ctx->K + 127) / 128, 128, 0, ctx->stream>>>(ctx->alpha, ctx->K, ctx->e_dead);
+    st->n_launches++;
+    static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8};
+    static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32};
+    for (int li = 0; li < PARK_LISTS; ++li) {
+        if (NCs[li] > pc.nc) continue;
+        const int NC = NCs[li], G = Gs[li];
+        const void* fn = estep_narrow_lookup(NC, G);
+        if (!fn) return fail(ctx, "no narrow-stage kernel for NC=%d G=%d", NC, G);
+        const int smem = 4 * (32 * (NC + 2) + (32 / G) * NC + (32 / G) * 16) * (int)sizeof(double);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 128, smem, 0));
+        if (occ < 1) return fail(ctx, "internal: zero occupancy for the narrow stage NC=%d G=%d", NC, G);
+        // the list length is only known on the device: size the grid for the documents that could be there
+        long long grid = (long long)ctx->prop.multiProcessorCount * occ;
+        grid = std::max<long long>(1, std::min<long long>(grid, (cp.D * G + 127) / 128));
+        NParams p;
+        memset(&p, 0, sizeof p);
+        p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+        p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.e_dead = ctx->e_dead;
+        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+        p.K = ctx->K; p.KP = ctx->KP; p.max_iter = max_iter; p.tol = tol;
+        p.lg_alpha = ctx->lg_alpha; p.alpha_sum = ctx->alpha_sum;
+        p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 8 + li;
+        p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
+        p.exact_phi = pc.exact_phi; p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
+        void* args[] = {&p};
+        timer.begin(ctx->stream, "narrow<%d,%d> smem=%d grid=%lld", NC, G, smem, grid);
+        CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(128), args, (size_t)smem, ctx->stream));
+        timer.end(ctx->stream);
+        st->n_launches++;
+        st->n_estep_launches++;
+    }
+    return 0;
+}
+
 int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
     const int K = ctx->K, KP = ctx->KP;
     int LK = 0, J = 0, LK1 = 0, J1 = 0;
@@ -606,6 +681,8 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         return std::partition_point(ns.begin(), ns.end(), [&](int n) { return n > limit; }) - ns.begin();
     };
     CK(cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->park_ctr, 0, 16 * sizeof(int), ctx->stream));
+    const ParkCfg pc = park_config(ctx);
     for (int i = 0; i < NC; ++i) cls[i].lo = first_leq(cls[i].cap);
     for (int i = 0; i < NC; ++i) cls[i].hi = (i + 1 < NC) ? cls[i + 1].lo : D;
     long long nlong = NC ? cls[0].lo : D;          // documents [0, nlong) fit no single-CTA class
@@ -730,6 +807,9 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             const char* ce = getenv("PYLDA_COMPACT");
             p.compact = !(ce && !strcmp(ce, "0"));
             p.revived = ctx->counters + 14;
+            p.park_nc = (c.kind == 1) ? pc.nc : 0;
+            p.park_rec = cp.park_rec; p.park_gam = cp.park_gam; p.park_lists = cp.park_lists;
+            p.park_counts = ctx->park_ctr; p.park_cap = (int)cp.D;
         }
         p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
         p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
@@ -741,6 +821,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         st->n_launches++;
         st->n_estep_launches++;
     }
+    if (pc.nc > 0 && launch_narrow(ctx, cp, pc, max_iter, tol, st, timer)) return 1;
     timer.report(ctx->stream);
     return 0;
 }
@@ -753,6 +834,11 @@ int ensure_outputs(pylda_ctx* ctx, Corpus& cp) {
     }
     if (!cp.docterm) CK(dalloc(&cp.docterm, (size_t)cp.D));
     if (!cp.iters) CK(dalloc(&cp.iters, (size_t)cp.D));
+    if (!cp.park_rec) {
+        CK(dalloc(&cp.park_rec, (size_t)cp.D * PARK_REC));
+        CK(dalloc(&cp.park_gam, (size_t)cp.D * PARK_GAM));
+        CK(dalloc(&cp.park_lists, (size_t)cp.D * PARK_LISTS));
+    }
     return 0;
 }
 
@@ -793,6 +879,9 @@ int pylda_create(pylda_ctx** out, int device) {
     cudaMalloc((void**)&ctx->scal, 8 * sizeof(double));
     cudaMemset(ctx->scal, 0, 8 * sizeof(double));
     cudaMalloc((void**)&ctx->counters, 16 * sizeof(int));
+    cudaMemset(ctx->counters, 0, 16 * sizeof(int));
+    cudaMalloc((void**)&ctx->park_ctr, 16 * sizeof(int));
+    cudaMemset(ctx->park_ctr, 0, 16 * sizeof(int));
     *out = ctx;
     return 0;
 }
@@ -805,7 +894,7 @@ int pylda_destroy(pylda_ctx* ctx) {
     free_corpus(ctx->corp[0]);
     free_corpus(ctx->corp[1]);
     free_model(ctx);
-    cudaFree(ctx->scal); cudaFree(ctx->partial); cudaFree(ctx->counters);
+    cudaFree(ctx->scal); cudaFree(ctx->partial); cudaFree(ctx->counters); cudaFree(ctx->park_ctr);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -893,6 +982,9 @@ static int set_alpha_host(pylda_ctx* ctx, const double* alpha_K) {
         lg += lgamma(alpha_K[k]);
     }
     ctx->alpha_max = amax;
+    ctx->alpha_min = *std::min_element(alpha_K, alpha_K + K);
+    ctx->alpha_sum = asum;
+    ctx->lg_alpha = lg;
     ctx->alpha_term = lgamma(asum) - lg;     // variational_bayes.py:195, per document
     CK(cudaMemcpyAsync(ctx->alpha, alpha_K, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
@@ -918,6 +1010,7 @@ int pylda_set_model(pylda_ctx* ctx, int K, int V, const double* eta_KxV, const d
         CK(dalloc(&ctx->phi_KV, kv));
         CK(dalloc(&ctx->kbuf, (size_t)4 * K));
         CK(dalloc(&ctx->alpha_ss, (size_t)K));
+        CK(dalloc(&ctx->e_dead, (size_t)K));
         for (auto& cp : ctx->corp) cp.has_results = false;
     }
     CK(cudaMemcpyAsync(ctx->eta, eta_KxV, (size_t)K * V * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1021,9 +1114,12 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     st.docs_at_cap = (int64_t)llround(ctx->last_scal[4]);
     st.row_trips = ctx->last_scal[5];
     {
-        int rv = 0;
+        int rv = 0, pk[8] = {0};
         cudaMemcpy(&rv, ctx->counters + 14, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(pk, ctx->park_ctr, sizeof pk, cudaMemcpyDeviceToHost);
         st.revived_docs = rv;
+        st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2];
+        st.docs_narrow = (long long)pk[3] + pk[4] + pk[5] + pk[6];
     }
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;
     st.algo_total_bytes = st.algo_read_bytes + 8.0 * (double)cp.D * K + 8.0 * (double)cp.nnz * K;

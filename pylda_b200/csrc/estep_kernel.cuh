@@ -57,6 +57,13 @@ struct EParams {
     int nmax;                        // tile capacity in rows (RES only)
     int compact;                     // estep_rt: dead-topic elimination enabled
     int* revived;                    // estep_rt: counter of documents in which an eliminated topic came back
+    // hand-over to the narrow stages (estep_narrow.cuh); park_nc = 0: off, 16 / 8: live-topic threshold
+    int park_nc;
+    int* park_rec;                   // PARK_REC ints per document
+    double* park_gam;                // PARK_GAM doubles per document
+    int* park_lists;                 // PARK_LISTS lists of park_cap documents
+    int* park_counts;
+    int park_cap;
     int group_bytes;                 // bytes of shared memory per group
     int off_groups;                  // byte offset of group 0 (after the CTA-wide alpha copy)
     int off_gam, off_spart, off_red, off_cnt, off_mwr, off_rid, off_tile;   // within a group

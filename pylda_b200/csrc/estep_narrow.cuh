@@ -1,0 +1,329 @@
+// Per-document VB E-step kernel, "narrow" stages (sm_100a): documents whose live topics fit 16 / 8 columns.
+//
+// Same mathematics as the other generations (reference variational_bayes.py:174-207 in product form).  Why it
+// exists: at the cold state of the headline config a short document spends 30-40 of its ~44 trips with
+// fewer than 8 topics alive (gamma_k != alpha_k; scripts/sim_live.py), yet the register-tile kernel keeps a
+// whole warp (or W warps) on it and pays ~250 warp instructions per trip for ~10 useful DFMA
+// (profiles/r1f_estep_rt_block_view.txt: the 32-column compact trip block is 40 % of the one-warp kernel).
+// estep_rt therefore PARKS a document once at most 16 (n <= 96) or 8 topics are alive: it writes gamma
+// (final for every dead topic), the trip count and the live columns, and moves on.  The kernels here pick the
+// parked documents up: G = 4..32 lanes per document (32/G documents per warp), a lane keeps RPL rows x NC live
+// columns of the document's tile in registers (48 doubles: 6 x 8 or 3 x 16), gathered directly from the
+// (V, KP) table.  A trip is RPL*NC DFMA for the norms (no cross-lane reduction: a lane owns whole rows),
+// RPL reciprocals, RPL*NC DFMA for the column sums, one reduce-scatter of NC values through shared memory,
+// NC/G exp(psi) per owner lane -- about 35 (G = 4) to 60 (G = 8) warp instructions per document-trip.
+// The 16-column stage hands a document over to the 8-column stage the same way.
+//
+// phi: a topic eliminated as dead (gamma_k == alpha_k bit for bit) satisfies e_k * s_k < ulp(alpha_k) / 2,
+// and e_k * s_k IS the document's total phi mass on that topic (sum_n c_n phi_nk).  The narrow stages
+// scatter the live columns only (red.global.add.f64 from registers); with exact_phi set they also add the
+// dead columns (w_n * B[w_n,k] * exp(psi(alpha_k)), < 1e-18 per document and topic) so that every entry of
+// phi_ss receives what the reference adds (variational_bayes.py:207).
+#pragma once
+#include "estep_kernel.cuh"
+
+namespace pylda {
+
+constexpr int PARK_REC = 20;    // ints per parked document: [0] trips done, [1] live topics, [2..18) their columns
+constexpr int PARK_GAM = 16;    // doubles per parked document: gamma of the live topics (same order)
+constexpr int PARK_LISTS = 7;   // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96); 8-column stage: G = 4, 8, 16, 32
+
+// list a parked document joins: by stage (live topics) and length
+__device__ __forceinline__ int park_list_index(int nlive, int n) {
+    if (nlive > 8) return n <= 24 ? 0 : n <= 48 ? 1 : 2;
+    return n <= 24 ? 3 : n <= 48 ? 4 : n <= 96 ? 5 : 6;
+}
+
+struct NParams {
+    const long long* __restrict__ row_ptr;
+    const int* __restrict__ ids;
+    const int* __restrict__ cts;
+    const double* __restrict__ Bt;
+    const double* __restrict__ mw;
+    const double* __restrict__ alpha;
+    const double* __restrict__ e_dead;   // exp(psi(alpha_k)): e of an eliminated topic (exact_phi)
+    double* gamma;
+    double* phi_ss;
+    double* docterm;
+    int* iters;
+    int K, KP, max_iter;
+    double tol;
+    double lg_alpha;                     // sum_k lgamma(alpha_k)
+    double alpha_sum;                    // sum_k alpha_k
+    const int* list;                     // documents of this class
+    const int* count;
+    int* head;                           // queue head
+    int* rec;                            // park records (PARK_REC ints per document)
+    double* gam;                         // gamma of the live topics (PARK_GAM doubles per document)
+    int* lists;                          // all PARK_LISTS lists (hand-over 16 -> 8 columns)
+    int* counts;
+    int cap;                             // capacity of one list
+    int exact_phi;
+    double chk_bound;                    // sum_n w_n <= chk_bound proves that no eliminated topic can come back
+    int* revived;                        // counter of documents in which one would have
+};
+
+template <int NC, int G>
+__global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
+    constexpr int RPL = 48 / NC;                      // rows per lane
+    constexpr int NG = 32 / G;                        // documents per warp
+    constexpr int SPL = (NC >= G) ? NC / G : 1;       // topic slots per owner lane
+    constexpr int NOWN = (NC >= G) ? G : NC;          // owner lanes per document
+    constexpr int PST = NC + 2;                       // padded stride of a lane's column partials (doubles)
+    constexpr int WSM = 32 * PST + NG * NC + NG * 16; // doubles per warp: partials, e, live-column bit masks
+    extern __shared__ __align__(16) double nsm[];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane / G, gl = lane % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
+    double* sp = nsm + (size_t)wid * WSM;
+    double* se = sp + 32 * PST + g * NC;
+    unsigned* lm = reinterpret_cast<unsigned*>(sp + 32 * PST + NG * NC) + g * 32;
+    const int K = p.K, KP = p.KP;
+    const double tolK = p.tol * (double)K;
+    const int ndocs = *p.count;
+    const bool owner = gl < NOWN;
+
+    while (true) {
+        int b0 = 0;
+        if (lane == 0) b0 = atomicAdd(p.head, NG);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        if (b0 >= ndocs) break;
+        const int idx = b0 + g;
+        const bool active = idx < ndocs;
+        int d = 0, n = 0, it = 0, nlive = 0;
+        long long base = 0;
+        const int* rec = p.rec;
+        if (active) {
+            d = p.list[idx];
+            base = p.row_ptr[d];
+            n = (int)(p.row_ptr[d + 1] - base);
+            rec = p.rec + (size_t)d * PARK_REC;
+            it = rec[0];
+            nlive = rec[1];
+        }
+        // ---- the lane's rows: RPL rows x NC live columns, gathered from the (V, KP) table ----
+        double bt[RPL][NC], c[RPL];
+        int id[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const int r = gl + G * i;
+            const bool ok = active && r < n;
+            id[i] = ok ? p.ids[base + r] : 0;
+            c[i] = ok ? (double)p.cts[base + r] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int col = (active && j < nlive) ? rec[2 + j] : 0;
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) bt[i][j] = p.Bt[(size_t)id[i] * KP + col];
+        }
+        // ---- owner lanes: SPL topic slots each ----
+        double al[SPL], gm[SPL], eo[SPL];
+        int ck[SPL];
+        bool ov[SPL];
+#pragma unroll
+        for (int u = 0; u < SPL; ++u) {
+            const int slot = gl * SPL + u;
+            ov[u] = owner && active && slot < nlive;
+            ck[u] = ov[u] ? rec[2 + slot] : 0;
+            al[u] = ov[u] ? p.alpha[ck[u]] : 1.0;
+            gm[u] = ov[u] ? p.gam[(size_t)d * PARK_GAM + slot] : 1.0;
+            eo[u] = ov[u] ? exp_digamma(gm[u]) : 0.0;
+            if (owner) se[slot] = eo[u];
+        }
+        __syncwarp(gmask);
+
+        double w[RPL], part[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) w[i] = 0.0, part[i] = 1.0;
+        bool fin = !active, parked = false;
+        while (!fin) {
+            // norm_n = B[n, live] . e   (a lane owns whole rows: no cross-lane reduction)
+            {
+                double a0[RPL], a1[RPL];
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) a0[i] = a1[i] = 0.0;
+#pragma unroll
+                for (int j = 0; j < NC; j += 2) {
+                    const double2 ev = *reinterpret_cast<const double2*>(se + j);
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) {
+                        a0[i] = fma(bt[i][j], ev.x, a0[i]);
+                        a1[i] = fma(bt[i][j + 1], ev.y, a1[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) part[i] = a0[i] + a1[i];
+            }
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) w[i] = (c[i] > 0.0) ? c[i] * rcp_nr(part[i]) : 0.0;
+            // column partial sums of this lane -> shared memory
+#pragma unroll
+            for (int j = 0; j < NC; j += 2) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) {
+                    s0 = fma(w[i], bt[i][j], s0);
+                    s1 = fma(w[i], bt[i][j + 1], s1);
+                }
+                *reinterpret_cast<double2*>(sp + lane * PST + j) = make_double2(s0, s1);
+            }
+            __syncwarp(gmask);
+            // owners: gamma update (:185), |d gamma| (:187), next e
+            double dd = 0.0, en[SPL];
+            bool lv[SPL];
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                const int slot = gl * SPL + u;
+                double t0 = 0.0, t1 = 0.0;
+                if (owner) {
+#pragma unroll
+                    for (int q = 0; q < G; q += 2) {
+                        t0 += sp[(g * G + q) * PST + slot];
+                        t1 += sp[(g * G + q + 1) * PST + slot];
+                    }
+                }
+                const double gn = fma(eo[u], t0 + t1, al[u]);
+                if (ov[u]) {
+                    dd += fabs(gn - gm[u]);
+                    gm[u] = gn;                                           // :188
+                }
+                lv[u] = ov[u] && gn != al[u];
+                en[u] = exp_digamma(ov[u] ? gn : 1.0);
+            }
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) dd += __shfl_xor_sync(gmask, dd, o);
+            ++it;
+            fin = dd <= tolK || it >= p.max_iter;                         // :189-190 / :174
+            if (!fin && NC == 16) {
+                // hand-over to the 8-column stage once at most 8 topics are alive
+                unsigned bal[SPL];
+                int nl = 0;
+#pragma unroll
+                for (int u = 0; u < SPL; ++u) {
+                    bal[u] = __ballot_sync(gmask, lv[u]) & gmask;
+                    nl += __popc(bal[u]);
+                }
+                if (nl <= 8) {
+                    int* wrec = p.rec + (size_t)d * PARK_REC;
+                    const unsigned below = gmask & ((1u << lane) - 1u);
+                    int rank = 0;
+#pragma unroll
+                    for (int u = 0; u < SPL; ++u) rank += __popc(bal[u] & below);
+#pragma unroll
+                    for (int u = 0; u < SPL; ++u) {
+                        if (ov[u]) p.gamma[(size_t)d * K + ck[u]] = gm[u];   // final for the topics that just died
+                        if (lv[u]) {
+                            wrec[2 + rank] = ck[u];
+                            p.gam[(size_t)d * PARK_GAM + rank] = gm[u];
+                            ++rank;
+                        }
+                    }
+                    if (gl == 0) {
+                        wrec[0] = it;
+                        wrec[1] = nl;
+                        const int li = park_list_index(nl, n);
+                        const int slot = atomicAdd(p.counts + li, 1);
+                        p.lists[(size_t)li * p.cap + slot] = d;
+                    }
+                    parked = true;
+                    fin = true;
+                }
+            }
+            if (!fin) {
+#pragma unroll
+                for (int u = 0; u < SPL; ++u) {
+                    eo[u] = ov[u] ? en[u] : 0.0;
+                    if (owner) se[gl * SPL + u] = eo[u];
+                }
+                __syncwarp(gmask);
+            }
+        }
+
+        // ---- epilogue (all documents of the warp together; w / part / se are those of the last trip) ----
+        const bool fini = active && !parked;
+        double t1 = 0.0, sgd = 0.0;
+        if (fini) {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+                if (c[i] > 0.0) t1 = fma(c[i], p.mw[id[i]] + log(part[i]), t1);   // sum_n c_n logsumexp_n
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                if (ov[u]) {
+                    const double dk = gm[u] - al[u];
+                    p.gamma[(size_t)d * K + ck[u]] = gm[u];                   // :212 / :216
+                    if (dk != 0.0) {
+                        t1 += lgamma(gm[u]) - lgamma(al[u]);                  // :197 (dead topics: lgamma(alpha_k), in lg_alpha)
+                        if (eo[u] > 0.0) t1 -= log(eo[u]) * dk;               // - sum_k psi_k sum_n c_n phi_nk
+                        sgd += dk;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            t1 += __shfl_xor_sync(gmask, t1, o);
+            sgd += __shfl_xor_sync(gmask, sgd, o);
+        }
+        if (fini && gl == 0) {
+            p.docterm[d] = t1 + p.lg_alpha - lgamma(p.alpha_sum + sgd);       // - lgamma(sum_k gamma_k), :197
+            p.iters[d] = it;
+        }
+        if (fini) {
+            // c_n phi_nk of the live columns (:207)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                if (j < nlive) {
+                    const int col = rec[2 + j];
+                    const double ej = se[j];
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i)
+                        if (c[i] > 0.0) atomicAdd(p.phi_ss + (size_t)id[i] * KP + col, w[i] * bt[i][j] * ej);
+                }
+            }
+        }
+        // Validation of the elimination: a dead topic stays dead while alpha_k + e_k s_k == alpha_k, s_k =
+        // sum_n w_n B[n,k] <= sum_n w_n (B <= 1).  The bound is checked first; only when it fails (or with
+        // exact_phi, which needs the pass anyway) the column sums of the eliminated topics are formed.
+        double ws = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) ws += w[i];
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) ws += __shfl_xor_sync(gmask, ws, o);
+        const bool full_pass = fini && (p.exact_phi || !(ws <= p.chk_bound));
+        if (__any_sync(gmask, full_pass)) {
+            for (int x = gl; x < 32; x += G) lm[x] = 0u;
+            __syncwarp(gmask);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u)
+                if (ov[u]) atomicOr(lm + (ck[u] >> 5), 1u << (ck[u] & 31));
+            __syncwarp(gmask);
+            bool came_back = false;
+            for (int k0 = 0; k0 < K; k0 += G) {
+                const int k = k0 + gl;
+                const bool dead = k < K && !((lm[k >> 5] >> (k & 31)) & 1u);
+                const double ed = dead ? p.e_dead[k] : 0.0;
+                double sk = 0.0;
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) {
+                    for (int q = 0; q < G; ++q) {
+                        const double wq = __shfl_sync(gmask, w[i], g * G + q);
+                        const int idq = __shfl_sync(gmask, id[i], g * G + q);
+                        if (dead && q + G * i < n) {
+                            const double bv = p.Bt[(size_t)idq * KP + k];
+                            sk = fma(wq, bv, sk);
+                            // ... with exact_phi the eliminated columns are scattered too (e_k = exp(psi(alpha_k)) for good)
+                            if (p.exact_phi) atomicAdd(p.phi_ss + (size_t)idq * KP + k, wq * bv * ed);
+                        }
+                    }
+                }
+                if (dead && fma(ed, sk, p.alpha[k]) != p.alpha[k]) came_back = true;
+            }
+            if (__any_sync(gmask, came_back) && gl == 0 && p.revived) atomicAdd(p.revived, 1);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace pylda

@@ -15,6 +15,7 @@
 // longer documents use estep_v2 (shared-memory tile) or the streaming kernel.
 #pragma once
 #include "estep_v2.cuh"
+#include "estep_narrow.cuh"
 
 namespace pylda {
 
@@ -44,7 +45,8 @@ struct RtCfg {
 template <int LK, int J, int W, int RMAX, int RU>
 __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* spart, double* red, const double* cnt,
                                         const double* mwr, double* tile, int n, int g, int gt, int gw, int lane,
-                                        bool warp_owns, const double* als, double* gams, double& lacc_out) {
+                                        bool warp_owns, const double* als, double* gams, double& lacc_out, int d,
+                                        int& park_nl) {
     using C = RtCfg<LK, J, W, RMAX>;
     constexpr int LN = C::LN, R = C::R, KPAD = C::KPAD, GT = C::GT, U = C::U, NB = C::NB, NP = C::NP;
     constexpr int RA = RU > 0 ? RU : 1;
@@ -316,11 +318,36 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                 if (!done) {
                     et = enc;
                     es_c[lane] = valid ? enc : 0.0;
+                    if (p.park_nc > 0 && n <= 192) {
+                        // few enough topics alive: park the document for the narrow stages (estep_narrow.cuh)
+                        const unsigned lvb = __ballot_sync(0xffffffffu, valid && gnc != alt);
+                        const int nl2 = __popc(lvb);
+                        if (nl2 >= 1 && nl2 <= (n <= 96 ? p.park_nc : 8)) {
+                            int* rec = p.park_rec + (size_t)d * PARK_REC;
+                            if ((lvb >> lane) & 1u) {
+                                const int rank = __popc(lvb & ((1u << lane) - 1u));
+                                rec[2 + rank] = kt;
+                                p.park_gam[(size_t)d * PARK_GAM + rank] = gnc;
+                            }
+                            if (lane == 0) {
+                                rec[0] = it;
+                                rec[1] = nl2;
+                            }
+                            park_nl = nl2;
+                            done = true;
+                        }
+                    }
                 }
-                if (W > 1 && lane == 0) red[0] = done ? 1.0 : 0.0;
+                if (W > 1 && lane == 0) {
+                    red[0] = done ? 1.0 : 0.0;
+                    red[1] = (double)park_nl;
+                }
             }
             gsync<W>(g);
-            if (W > 1) done = red[0] != 0.0;
+            if (W > 1) {
+                done = red[0] != 0.0;
+                park_nl = (int)red[1];
+            }
             if (done) break;
         }
         // back to the full-width arrays: gamma, and the e of the LAST trip into the buffer the final pass reads
@@ -329,6 +356,10 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
             es2[((it - 1) & 1) * KPAD + kt] = et;
         }
         gsync<W>(g);
+        if (park_nl > 0) {                                                // parked: the narrow stages finish it
+            lacc_out = 0.0;
+            return it;
+        }
     }
 
     // ---- phi from the LAST e (buffer (it-1)&1; w[] and part[] are those of the last trip) -------
@@ -500,12 +531,12 @@ __global__ void __launch_bounds__(NWARPS * 32) estep_rt(const EParams p) {
         int RU = (NG - gw + W - 1) / W;
         RU = RU < 0 ? 0 : (RU > R ? R : RU);
         double lacc = 0.0;
-        int it = 0;
+        int it = 0, park_nl = 0;
 #define PYLDA_RT_CASE(X)                                                                                     \
     case X:                                                                                                  \
         if constexpr (X <= R)                                                                                \
             it = rt_trips<LK, J, W, RMAX, X>(p, es2, spart, red, cnt, mwr, tile, n, g, gt, gw, lane, warp_owns, als, \
-                                       gams, lacc);                                                          \
+                                       gams, lacc, d, park_nl);                                              \
         break;
         switch (RU) {
             PYLDA_RT_CASE(0) PYLDA_RT_CASE(1) PYLDA_RT_CASE(2) PYLDA_RT_CASE(3) PYLDA_RT_CASE(4)
@@ -513,6 +544,21 @@ __global__ void __launch_bounds__(NWARPS * 32) estep_rt(const EParams p) {
         }
 #undef PYLDA_RT_CASE
         fence_async_smem();   // generic-proxy writes of phi -> visible to the bulk-async engine
+        if (park_nl > 0) {
+            // parked: gamma so far (final for every dead topic) and the document joins its narrow-stage list
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = gt + GT * u;
+                if (k < K) p.gamma[(size_t)d * K + k] = gams[k];
+            }
+            if (gt == 0) {
+                const int li = park_list_index(park_nl, n);
+                const int slot = atomicAdd(p.park_counts + li, 1);
+                p.park_lists[(size_t)li * p.park_cap + slot] = d;
+            }
+            gsync<W>(g);
+            continue;
+        }
 
         // ---- per-document ELBO pieces and gamma write-back ------------------------------------
         double t1 = lacc, sg = 0.0;

@@ -236,4 +236,11 @@ __global__ void k_special(int which, long long n, const double* __restrict__ x, 
            : which == 3 ? rcp_nr(v) : exp_digamma(v);
 }
 
+// exp(psi(alpha_k)) with the device function the E-step kernels use: the e of a topic eliminated as dead
+// (gamma_k == alpha_k), read by the narrow stages (estep_narrow.cuh)
+__global__ void k_e_dead(const double* __restrict__ alpha, int K, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) out[k] = exp_digamma(alpha[k]);
+}
+
 }  // namespace pylda

@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -35,6 +35,8 @@ class Stats(ctypes.Structure):
         ("docs_streamed", ctypes.c_int64),
         ("row_trips", ctypes.c_double),
         ("revived_docs", ctypes.c_int64),
+        ("docs_narrow_wide", ctypes.c_int64),
+        ("docs_narrow", ctypes.c_int64),
     ]
 
     def as_dict(self):
