@@ -123,6 +123,7 @@ struct pylda_ctx {
     int* counters = nullptr;     // class queue heads
     int* park_ctr = nullptr;     // narrow stages: list lengths [0..8) and queue heads [8..16)
     double* e_dead = nullptr;    // (K,) exp(psi(alpha_k))
+    double* wsum = nullptr;      // (V,) row weights of the documents finished by the narrow stages
     bool model_set = false;
     bool phi_KV_valid = false;
     bool have_alpha_ss = false;
@@ -168,8 +169,8 @@ void free_corpus(Corpus& c) {
 
 void free_model(pylda_ctx* c) {
     cudaFree(c->eta); cudaFree(c->alpha); cudaFree(c->Elt); cudaFree(c->Bt); cudaFree(c->mw);
-    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss); cudaFree(c->e_dead);
-    c->eta = c->alpha = c->Elt = c->Bt = c->mw = c->phi = c->phi_KV = c->kbuf = c->alpha_ss = c->e_dead = nullptr;
+    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss); cudaFree(c->e_dead); cudaFree(c->wsum);
+    c->eta = c->alpha = c->Elt = c->Bt = c->mw = c->phi = c->phi_KV = c->kbuf = c->alpha_ss = c->e_dead = c->wsum = nullptr;
     c->model_set = false;
 }
 
@@ -570,15 +571,13 @@ double host_digamma(double x) {
 // e_k s_k < ulp(alpha_k)/2, s_k <= sum_n w_n; chk_bound = alpha_min 2^-54 / exp(psi(alpha_max)) is the value
 // of sum_n w_n below which that is certain.  The hand-over is only used when the bound leaves three orders
 // of magnitude of room (alpha <~ 0.02); the kernels check every document against it.
-struct ParkCfg { int nc; int exact_phi; double chk_bound; };
+struct ParkCfg { int nc; double chk_bound; };
 ParkCfg park_config(const pylda_ctx* ctx) {
     ParkCfg c;
     const char* e = getenv("PYLDA_PARK");
     c.nc = 16;
     if (e && *e) c.nc = atoi(e);
     if (c.nc != 8 && c.nc != 16) c.nc = 0;
-    const char* x = getenv("PYLDA_EXACT_PHI");
-    c.exact_phi = (x && !strcmp(x, "1")) ? 1 : 0;
     const double ed = exp(host_digamma(ctx->alpha_max));
     c.chk_bound = ed > 0.0 ? ctx->alpha_min * ldexp(1.0, -54) / ed : HUGE_VAL;
     if (!(c.chk_bound >= 1e3)) c.nc = 0;
@@ -589,6 +588,7 @@ ParkCfg park_config(const pylda_ctx* ctx) {
 
 int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, double tol, pylda_stats* st, ClassTimer& timer) {
     k_e_dead<<<(ctx->K + 127) / 128, 128, 0, ctx->stream>>>(ctx->alpha, ctx->K, ctx->e_dead);
+    CK(cudaMemsetAsync(ctx->wsum, 0, (size_t)ctx->V * sizeof(double), ctx->stream));
     st->n_launches++;
     static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8};
     static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32};
@@ -609,12 +609,12 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         memset(&p, 0, sizeof p);
         p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
         p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.e_dead = ctx->e_dead;
-        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.wsum = ctx->wsum; p.docterm = cp.docterm; p.iters = cp.iters;
         p.K = ctx->K; p.KP = ctx->KP; p.max_iter = max_iter; p.tol = tol;
         p.lg_alpha = ctx->lg_alpha; p.alpha_sum = ctx->alpha_sum;
         p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 8 + li;
         p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
-        p.exact_phi = pc.exact_phi; p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
+        p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
         void* args[] = {&p};
         timer.begin(ctx->stream, "narrow<%d,%d> smem=%d grid=%lld", NC, G, smem, grid);
         CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(128), args, (size_t)smem, ctx->stream));
@@ -622,6 +622,12 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         st->n_launches++;
         st->n_estep_launches++;
     }
+    timer.begin(ctx->stream, "dead-topic statistics (k_dead_phi)");
+    k_dead_phi<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->Bt, ctx->wsum, ctx->e_dead, ctx->K, ctx->V,
+                                                                         ctx->KP, ctx->phi);
+    timer.end(ctx->stream);
+    CK(cudaGetLastError());
+    st->n_launches++;
     return 0;
 }
 
@@ -1011,6 +1017,7 @@ int pylda_set_model(pylda_ctx* ctx, int K, int V, const double* eta_KxV, const d
         CK(dalloc(&ctx->kbuf, (size_t)4 * K));
         CK(dalloc(&ctx->alpha_ss, (size_t)K));
         CK(dalloc(&ctx->e_dead, (size_t)K));
+        CK(dalloc(&ctx->wsum, (size_t)V));
         for (auto& cp : ctx->corp) cp.has_results = false;
     }
     CK(cudaMemcpyAsync(ctx->eta, eta_KxV, (size_t)K * V * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

@@ -14,11 +14,12 @@
 // NC/G exp(psi) per owner lane -- about 35 (G = 4) to 60 (G = 8) warp instructions per document-trip.
 // The 16-column stage hands a document over to the 8-column stage the same way.
 //
-// phi: a topic eliminated as dead (gamma_k == alpha_k bit for bit) satisfies e_k * s_k < ulp(alpha_k) / 2,
-// and e_k * s_k IS the document's total phi mass on that topic (sum_n c_n phi_nk).  The narrow stages
-// scatter the live columns only (red.global.add.f64 from registers); with exact_phi set they also add the
-// dead columns (w_n * B[w_n,k] * exp(psi(alpha_k)), < 1e-18 per document and topic) so that every entry of
-// phi_ss receives what the reference adds (variational_bayes.py:207).
+// phi: for a parked document every topic outside the live columns has e_k = exp(psi(alpha_k)) =: ed_k for good, so
+//   c_n phi_nk = w_n B[n,k] e_k = w_n B[n,k] ed_k + [k live] w_n B[n,k] (e_k - ed_k).
+// The second term is scattered from registers (NC columns per row, red.global.add.f64); the first is summed
+// over all parked documents per WORD: the kernels add w_n to wsum[word] (one red per row instead of K) and
+// k_dead_phi adds ed_k B[w,k] wsum[w] to the statistics in one pass over the (V, KP) table.  Every entry of
+// phi_ss receives exactly what the reference adds (variational_bayes.py:207), re-associated.
 #pragma once
 #include "estep_kernel.cuh"
 
@@ -41,9 +42,10 @@ struct NParams {
     const double* __restrict__ Bt;
     const double* __restrict__ mw;
     const double* __restrict__ alpha;
-    const double* __restrict__ e_dead;   // exp(psi(alpha_k)): e of an eliminated topic (exact_phi)
+    const double* __restrict__ e_dead;   // exp(psi(alpha_k)): e of an eliminated topic
     double* gamma;
     double* phi_ss;
+    double* wsum;                        // (V,) sum of w_n over the parked documents' rows, per word
     double* docterm;
     int* iters;
     int K, KP, max_iter;
@@ -58,7 +60,6 @@ struct NParams {
     int* lists;                          // all PARK_LISTS lists (hand-over 16 -> 8 columns)
     int* counts;
     int cap;                             // capacity of one list
-    int exact_phi;
     double chk_bound;                    // sum_n w_n <= chk_bound proves that no eliminated topic can come back
     int* revived;                        // counter of documents in which one would have
 };
@@ -271,27 +272,31 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
             p.iters[d] = it;
         }
         if (fini) {
-            // c_n phi_nk of the live columns (:207)
+            // c_n phi_nk (:207): live columns from registers (minus the dead-topic value that k_dead_phi adds for
+            // every column), and the row weights for k_dead_phi
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 if (j < nlive) {
                     const int col = rec[2 + j];
-                    const double ej = se[j];
+                    const double ej = se[j] - p.e_dead[col];
 #pragma unroll
                     for (int i = 0; i < RPL; ++i)
                         if (c[i] > 0.0) atomicAdd(p.phi_ss + (size_t)id[i] * KP + col, w[i] * bt[i][j] * ej);
                 }
             }
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+                if (c[i] > 0.0) atomicAdd(p.wsum + id[i], w[i]);
         }
         // Validation of the elimination: a dead topic stays dead while alpha_k + e_k s_k == alpha_k, s_k =
-        // sum_n w_n B[n,k] <= sum_n w_n (B <= 1).  The bound is checked first; only when it fails (or with
-        // exact_phi, which needs the pass anyway) the column sums of the eliminated topics are formed.
+        // sum_n w_n B[n,k] <= sum_n w_n (B <= 1).  The bound is checked first; only when it fails the column
+        // sums of the eliminated topics are formed.
         double ws = 0.0;
 #pragma unroll
         for (int i = 0; i < RPL; ++i) ws += w[i];
 #pragma unroll
         for (int o = G >> 1; o > 0; o >>= 1) ws += __shfl_xor_sync(gmask, ws, o);
-        const bool full_pass = fini && (p.exact_phi || !(ws <= p.chk_bound));
+        const bool full_pass = fini && !(ws <= p.chk_bound);
         if (__any_sync(gmask, full_pass)) {
             for (int x = gl; x < 32; x += G) lm[x] = 0u;
             __syncwarp(gmask);
@@ -313,8 +318,6 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
                         if (dead && q + G * i < n) {
                             const double bv = p.Bt[(size_t)idq * KP + k];
                             sk = fma(wq, bv, sk);
-                            // ... with exact_phi the eliminated columns are scattered too (e_k = exp(psi(alpha_k)) for good)
-                            if (p.exact_phi) atomicAdd(p.phi_ss + (size_t)idq * KP + k, wq * bv * ed);
                         }
                     }
                 }

@@ -243,4 +243,20 @@ __global__ void k_e_dead(const double* __restrict__ alpha, int K, double* __rest
     if (k < K) out[k] = exp_digamma(alpha[k]);
 }
 
+// phi_ss[w,k] += ed_k B[w,k] wsum[w]: the statistics of the topics eliminated as dead, for all documents that
+// finished in the narrow stages (estep_narrow.cuh).  One thread per topic pair, words in the grid's y/loop.
+__global__ void k_dead_phi(const double* __restrict__ Bt, const double* __restrict__ wsum, const double* __restrict__ e_dead,
+                           int K, int V, int KP, double* __restrict__ phi) {
+    const int wpb = blockDim.x / 64;                       // words per block pass (64 threads per word)
+    const int t = threadIdx.x & 63, wl = threadIdx.x >> 6;
+    for (long long w = (long long)blockIdx.x * wpb + wl; w < V; w += (long long)gridDim.x * wpb) {
+        const double ws = wsum[w];
+        if (ws == 0.0) continue;
+        for (int k = t; k < K; k += 64) {
+            const size_t o = (size_t)w * KP + k;
+            phi[o] = fma(e_dead[k] * ws, Bt[o], phi[o]);
+        }
+    }
+}
+
 }  // namespace pylda

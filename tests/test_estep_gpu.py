@@ -319,3 +319,55 @@ def test_dead_topic_elimination_changes_nothing(ctx, monkeypatch):
     assert max_rel(fast["phi_ss"], full["phi_ss"], floor=PHI_FLOOR) <= 1e-10
     assert abs(fast["doc_ll"] - full["doc_ll"]) <= 1e-12 * abs(full["doc_ll"])
     assert fast["stats"]["kernel_ms"] < full["stats"]["kernel_ms"]
+
+
+def test_narrow_stages_change_nothing(ctx, monkeypatch):
+    """PYLDA_PARK=0 (every document finishes in the register-tile kernel) and the default (documents with at
+    most 16 / 8 live topics finish in the narrow stages, estep_narrow.cuh) must agree to rounding: identical
+    trip counts, gamma, ELBO -- and phi_ss down to its smallest entries: the statistics of the topics
+    eliminated as dead (~1e-44 per entry at alpha = 0.01) are added through the per-word weight sums."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 100, 20000
+    row_ptr, ids, cts = synthetic.synthetic_corpus(3000, V, seed=43, length="zipf")
+    eta = synthetic.initial_eta(K, V, 0)
+    alpha = numpy.full(K, 1.0 / K)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    monkeypatch.setenv("PYLDA_PARK", "0")
+    base = ctx.estep(0, eta, alpha, 50, 1e-6)
+    it_base = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    assert base["stats"]["docs_narrow"] == 0 and base["stats"]["docs_narrow_wide"] == 0
+    for park in ("16", "8"):
+        monkeypatch.setenv("PYLDA_PARK", park)
+        fast = ctx.estep(0, eta, alpha, 50, 1e-6)
+        it_fast = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+        st = fast["stats"]
+        print("park", park, "narrow", st["docs_narrow_wide"], st["docs_narrow"], "kernel ms", st["kernel_ms"], base["stats"]["kernel_ms"])
+        assert st["docs_narrow"] > 1000 and st["revived_docs"] == 0
+        assert (st["docs_narrow_wide"] > 1000) == (park == "16")
+        assert numpy.array_equal(it_base, it_fast)
+        assert max_rel(fast["gamma"], base["gamma"]) <= 1e-11
+        assert max_rel(fast["phi_ss"], base["phi_ss"], floor=1e-250) <= 1e-9      # relative, tiny entries included
+        assert abs(fast["doc_ll"] - base["doc_ll"]) <= 1e-12 * abs(base["doc_ll"])
+    # ... and against the oracle on a sub-corpus, again down to the tiny entries
+    sub = 400
+    rp, nz = row_ptr[:sub + 1], int(row_ptr[sub])
+    ref = O.e_step(rp, ids[:nz], cts[:nz], eta, alpha, 50, 1e-6, return_iters=True)
+    ctx.set_corpus(0, rp, ids[:nz], cts[:nz])
+    monkeypatch.delenv("PYLDA_PARK")
+    out = ctx.estep(0, eta, alpha, 50, 1e-6)
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "narrow vs oracle")
+    assert out["stats"]["docs_narrow"] > 100
+    assert max_rel(out["phi_ss"], ref["phi_ss"], floor=1e-250) <= RTOL
+    assert numpy.array_equal(ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"], ref["iters"])
+
+
+def test_narrow_stages_off_when_alpha_is_large(ctx):
+    """The hand-over relies on exp(psi(alpha_k)) being far below ulp(alpha_k): with alpha = 0.05 the safety
+    bound disables it (topics then never die bit for bit either)."""
+    from pylda_b200 import synthetic
+    K, V = 100, 5000
+    row_ptr, ids, cts = synthetic.synthetic_corpus(200, V, seed=44, length="zipf")
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, synthetic.initial_eta(K, V, 0), numpy.full(K, 0.05), 50, 1e-6)
+    assert out["stats"]["docs_narrow"] == 0 and out["stats"]["docs_narrow_wide"] == 0
