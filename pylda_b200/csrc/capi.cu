@@ -326,6 +326,26 @@ GroupLayout group_layout_cl(int KPAD, int cap, int ST) {
     return g;
 }
 
+// shared-memory layout of one CTA of estep_hy (8 warps; `cap` rows in shared memory, `capr` in registers,
+// C CTAs per cluster)
+GroupLayout group_layout_hy(int LK, int KPAD, int C, int capr, int cap, int ST) {
+    GroupLayout g;
+    const int W = 8, LN = 32 / LK;
+    int o = 16;
+    o += 2 * KPAD * 8;                // e, double buffered
+    g.off_spart = o; o += W * LN * KPAD * 8;
+    g.off_red = o;   o += align_up(4 * W + 2, 2) * 8;
+    g.off_gam = o;   o += (C > 1 ? 2 * C * KPAD * 8 : 0);   // exchange slots [2][C][KPAD]
+    const int rows = capr + cap + LN;
+    g.off_cnt = o;   o += rows * 8;
+    g.off_mwr = o;   o += rows * 8;
+    g.off_rid = o;   o += rows * 4;
+    o = align_up(o, 16);
+    g.off_tile = o;  o += std::max(cap, capr) * ST * 8 + KPAD * 8;
+    g.bytes = align_up(o, 128);
+    return g;
+}
+
 int ensure_partial(pylda_ctx* ctx, size_t n) {
     if (ctx->partial_cap >= n) return 0;
     CK(dalloc(&ctx->partial, n));
@@ -435,10 +455,11 @@ int launch_estep_v1(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_
 // PYLDA_CLASSES overrides the default list (tuning aid).
 struct ClassCfg { int kind, W, G, R, LK, J; };
 
-std::vector<ClassCfg> class_config() {
+std::vector<ClassCfg> class_config(bool use_hy) {
     std::vector<ClassCfg> out;
     const char* env = getenv("PYLDA_CLASSES");
-    std::string spec = env && *env ? env : "8x1,r8,r4,r2,r1";
+    // with the hybrid kernel every document above the largest register-tile class is its business
+    std::string spec = env && *env ? env : use_hy ? "r8,r4,r2,r1" : "8x1,r8,r4,r2,r1";
     size_t pos = 0;
     while (pos < spec.size()) {
         size_t end = spec.find(',', pos);
@@ -550,6 +571,10 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
     p.K = K; p.KP = KP; p.ST = KP; p.max_iter = max_iter; p.tol = tol;
     p.W = W; p.nmax = cap; p.group_bytes = gl.bytes;
+    {
+        const char* z = getenv("PYLDA_ZIGZAG");                 // alternate the row order trip by trip (L1 reuse)
+        p.compact = !(z && !strcmp(z, "0"));
+    }
     p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt; p.off_rid = gl.off_rid;
     void* args[] = {&p};
     CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)gl.bytes, ctx->stream));
@@ -590,12 +615,19 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
     k_e_dead<<<(ctx->K + 127) / 128, 128, 0, ctx->stream>>>(ctx->alpha, ctx->K, ctx->e_dead);
     CK(cudaMemsetAsync(ctx->wsum, 0, (size_t)ctx->V * sizeof(double), ctx->stream));
     st->n_launches++;
-    static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8};
-    static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32};
-    for (int li = 0; li < PARK_LISTS; ++li) {
+    // launch order: the 16-column lists (0, 1, 2, 7) feed the 8-column ones (3..6)
+    static const int order[PARK_LISTS] = {0, 1, 2, 7, 3, 4, 5, 6};
+    static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8, 16};
+    static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32, 32};
+    static const int RPLs[PARK_LISTS] = {3, 3, 3, 6, 6, 6, 6, 6};
+    for (int oi = 0; oi < PARK_LISTS; ++oi) {
+        const int li = order[oi];
         if (NCs[li] > pc.nc) continue;
         const int NC = NCs[li], G = Gs[li];
-        const void* fn = estep_narrow_lookup(NC, G);
+        // CTAs per SM the kernel is compiled for: 2 (255 registers, no spills) or 3 (168 registers, tuning aid)
+        int minb = 2;
+        if (const char* e = getenv("PYLDA_NARROW_OCC")) minb = (atoi(e) == 3 && RPLs[li] * NC <= 48) ? 3 : 2;
+        const void* fn = estep_narrow_lookup(NC, G, RPLs[li], minb);
         if (!fn) return fail(ctx, "no narrow-stage kernel for NC=%d G=%d", NC, G);
         const int smem = 4 * (32 * (NC + 2) + (32 / G) * NC + (32 / G) * 16) * (int)sizeof(double);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -616,7 +648,7 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
         p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
         void* args[] = {&p};
-        timer.begin(ctx->stream, "narrow<%d,%d> smem=%d grid=%lld", NC, G, smem, grid);
+        timer.begin(ctx->stream, "narrow<%d,%d,%d> smem=%d grid=%lld", NC, G, RPLs[li], smem, grid);
         CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(128), args, (size_t)smem, ctx->stream));
         timer.end(ctx->stream);
         st->n_launches++;
@@ -642,6 +674,12 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     const int smem_budget = (int)ctx->prop.sharedMemPerBlockOptin;
     const char* kv = getenv("PYLDA_KERNEL");
     const bool use_rt = !(kv && !strcmp(kv, "v2"));
+    int R_hy = 0;
+    // The hybrid register / shared-memory cluster kernel keeps whole long documents on chip.  It is the default
+    // where a term row is so wide (K > 256) that no single-CTA class exists and everything would stream from L2;
+    // at K ~ 100 the streaming kernel is still faster (profiles/r2b_*), PYLDA_KERNEL=hybrid selects it anyway.
+    const bool want_hy = kv ? !strcmp(kv, "hybrid") : (K > 256);
+    const void* fn_hy = want_hy ? estep_hy_lookup(LK, J, &R_hy) : nullptr;
 
     // Candidate classes, each with a row capacity; a document goes to the class with the smallest
     // capacity that holds it.  kind 0 = estep_v2 (tile in shared memory), kind 1 = estep_rt (tile
@@ -649,7 +687,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     // shape (LK, J) is chosen per class.
     struct Cls { int kind, W, G, cap, LK, J; const void* fn; long long lo, hi; };
     std::vector<Cls> cls;
-    for (const ClassCfg& c : class_config()) {
+    for (const ClassCfg& c : class_config(fn_hy != nullptr)) {
         int lk = c.LK, j = c.J;
         if (lk > 0) {
             if (lk * j < (K + 1) / 2) continue;            // forced shape too narrow for K
@@ -697,6 +735,66 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     // The cluster path is correct (parity tests run it with PYLDA_KERNEL=cluster) but at 8 warps per SM
     // its per-trip serial phase (cluster barrier + exp(psi) + reductions) still costs more than
     // re-streaming from L2; it stays opt-in until that phase is shortened.
+    if (nlong > 0 && fn_hy) {
+        // hybrid register / shared-memory tile kernel: clusters of C = 1, 2, 4, 8 CTAs, carved from the short end
+        const int capr = 8 * LN * R_hy;
+        bool zeroed = false;
+        long long hi = nlong;
+        for (int C = 1; C <= 8 && hi > 0; C <<= 1) {
+            const GroupLayout g0 = group_layout_hy(LK, KPAD, C, 0, 0, ST);
+            int cap_s = (smem_budget - g0.bytes - 256 - (capr + LN) * 20) / (ST * 8 + 20);
+            cap_s = cap_s / LN * LN;
+            if (cap_s < capr) break;                    // the register rows leave through the shared-memory region
+            const int per_cta = capr + cap_s - LN;      // (the per-CTA slice is rounded up to LN rows)
+            const long long lo = first_leq(C * per_cta);
+            if (lo >= hi) continue;
+            const long long nd = hi - lo;
+            const GroupLayout gl = group_layout_hy(LK, KPAD, C, capr, cap_s, ST);
+            CK(cudaFuncSetAttribute(fn_hy, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.bytes));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = (size_t)gl.bytes;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            cfg.gridDim = dim3((unsigned)(C * ctx->prop.multiProcessorCount));
+            int ncl = 0;
+            if (C > 1) {
+                CK(cudaOccupancyMaxActiveClusters(&ncl, fn_hy, &cfg));
+                if (ncl < 1) break;                     // this cluster size cannot be scheduled: the rest streams
+            } else {
+                ncl = ctx->prop.multiProcessorCount;
+            }
+            ncl = (int)std::min<long long>(ncl, nd);
+            cfg.gridDim = dim3((unsigned)(ncl * C));
+            if (!zeroed) {
+                CK(cudaMemsetAsync(cp.docterm, 0, (size_t)std::max<long long>(D, 1) * sizeof(double), ctx->stream));
+                zeroed = true;
+            }
+            EParams p;
+            memset(&p, 0, sizeof p);
+            p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+            p.order = cp.order + lo; p.ndocs = (int)nd; p.counter = nullptr;
+            p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
+            p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+            p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
+            p.W = 8; p.nmax = cap_s; p.group_bytes = gl.bytes; p.off_groups = 0;
+            p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
+            p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
+            void* args[] = {&p};
+            timer.begin(ctx->stream, "hybrid<%d,%d,R%d> C=%d docs=%lld nmax=%d nmin=%d rows/CTA=%d+%d smem=%d clusters=%d", LK, J,
+                        R_hy, C, nd, ns[lo], ns[hi - 1], capr, cap_s, gl.bytes, ncl);
+            CK(cudaLaunchKernelExC(&cfg, fn_hy, args));
+            timer.end(ctx->stream);
+            st->n_launches++;
+            st->n_estep_launches++;
+            hi = lo;
+        }
+        nstream = hi;
+    }
     const void* fn_cl = (kv && !strcmp(kv, "cluster")) ? estep_cl_lookup(LK, J) : nullptr;
     if (nlong > 0 && fn_cl) {
         // cluster classes: C CTAs per document, each CTA keeps a slice of at most cap_cl rows resident
@@ -1125,7 +1223,7 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
         cudaMemcpy(&rv, ctx->counters + 14, sizeof(int), cudaMemcpyDeviceToHost);
         cudaMemcpy(pk, ctx->park_ctr, sizeof pk, cudaMemcpyDeviceToHost);
         st.revived_docs = rv;
-        st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2];
+        st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2] + pk[7];
         st.docs_narrow = (long long)pk[3] + pk[4] + pk[5] + pk[6];
     }
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;

@@ -27,11 +27,12 @@ namespace pylda {
 
 constexpr int PARK_REC = 20;    // ints per parked document: [0] trips done, [1] live topics, [2..18) their columns
 constexpr int PARK_GAM = 16;    // doubles per parked document: gamma of the live topics (same order)
-constexpr int PARK_LISTS = 7;   // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96); 8-column stage: G = 4, 8, 16, 32
+constexpr int PARK_LISTS = 8;   // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96) [0..2] and G = 32 with 6 rows per lane
+                                // (n <= 192) [7]; 8-column stage: G = 4, 8, 16, 32 (n <= 24, 48, 96, 192) [3..6]
 
 // list a parked document joins: by stage (live topics) and length
 __device__ __forceinline__ int park_list_index(int nlive, int n) {
-    if (nlive > 8) return n <= 24 ? 0 : n <= 48 ? 1 : 2;
+    if (nlive > 8) return n <= 24 ? 0 : n <= 48 ? 1 : n <= 96 ? 2 : 7;
     return n <= 24 ? 3 : n <= 48 ? 4 : n <= 96 ? 5 : 6;
 }
 
@@ -64,9 +65,9 @@ struct NParams {
     int* revived;                        // counter of documents in which one would have
 };
 
-template <int NC, int G>
-__global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
-    constexpr int RPL = 48 / NC;                      // rows per lane
+// RPL rows per lane: 48 / NC (96 registers of tile), or twice that; MINB CTAs per SM (register budget 65536 / (128 MINB))
+template <int NC, int G, int RPL, int MINB>
+__global__ void __launch_bounds__(128, MINB) estep_narrow(const NParams p) {
     constexpr int NG = 32 / G;                        // documents per warp
     constexpr int SPL = (NC >= G) ? NC / G : 1;       // topic slots per owner lane
     constexpr int NOWN = (NC >= G) ? G : NC;          // owner lanes per document
@@ -133,13 +134,18 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
             eo[u] = ov[u] ? exp_digamma(gm[u]) : 0.0;
             if (owner) se[slot] = eo[u];
         }
-        __syncwarp(gmask);
+        __syncwarp();
 
         double w[RPL], part[RPL];
 #pragma unroll
         for (int i = 0; i < RPL; ++i) w[i] = 0.0, part[i] = 1.0;
+        // The trip loop is WARP-uniform: it runs until every document of the warp has stopped.  A stopped document
+        // no longer updates gamma, e or its trip counter, so its extra trips recompute the same norms and weights
+        // (idempotent) -- no per-group control flow, full-mask __syncwarp / shuffles.  (Per-group masks made ptxas
+        // emit MATCH / BRA.DIV sequences and the groups ended up running the loop body separately: 2.3 passes per
+        // trip in profiles/r2c_narrow_blocks.txt.)
         bool fin = !active, parked = false;
-        while (!fin) {
+        while (true) {
             // norm_n = B[n, live] . e   (a lane owns whole rows: no cross-lane reduction)
             {
                 double a0[RPL], a1[RPL];
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
                 for (int i = 0; i < RPL; ++i) part[i] = a0[i] + a1[i];
             }
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) w[i] = (c[i] > 0.0) ? c[i] * rcp_nr(part[i]) : 0.0;
+            for (int i = 0; i < RPL; ++i) w[i] = c[i] * rcp_nr(c[i] > 0.0 ? part[i] : 1.0);   // branch-free: the reciprocals interleave
             // column partial sums of this lane -> shared memory
 #pragma unroll
             for (int j = 0; j < NC; j += 2) {
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
                 }
                 *reinterpret_cast<double2*>(sp + lane * PST + j) = make_double2(s0, s1);
             }
-            __syncwarp(gmask);
+            __syncwarp();
             // owners: gamma update (:185), |d gamma| (:187), next e
             double dd = 0.0, en[SPL];
             bool lv[SPL];
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
                     }
                 }
                 const double gn = fma(eo[u], t0 + t1, al[u]);
-                if (ov[u]) {
+                if (ov[u] && !fin) {
                     dd += fabs(gn - gm[u]);
                     gm[u] = gn;                                           // :188
                 }
@@ -194,19 +200,22 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
                 en[u] = exp_digamma(ov[u] ? gn : 1.0);
             }
 #pragma unroll
-            for (int o = G >> 1; o > 0; o >>= 1) dd += __shfl_xor_sync(gmask, dd, o);
-            ++it;
-            fin = dd <= tolK || it >= p.max_iter;                         // :189-190 / :174
-            if (!fin && NC == 16) {
+            for (int o = G >> 1; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            const bool running = !fin;
+            if (running) {
+                ++it;
+                fin = dd <= tolK || it >= p.max_iter;                     // :189-190 / :174
+            }
+            if (NC == 16) {
                 // hand-over to the 8-column stage once at most 8 topics are alive
                 unsigned bal[SPL];
                 int nl = 0;
 #pragma unroll
                 for (int u = 0; u < SPL; ++u) {
-                    bal[u] = __ballot_sync(gmask, lv[u]) & gmask;
+                    bal[u] = __ballot_sync(0xffffffffu, lv[u]) & gmask;
                     nl += __popc(bal[u]);
                 }
-                if (nl <= 8) {
+                if (running && !fin && nl <= 8) {
                     int* wrec = p.rec + (size_t)d * PARK_REC;
                     const unsigned below = gmask & ((1u << lane) - 1u);
                     int rank = 0;
@@ -238,8 +247,9 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
                     eo[u] = ov[u] ? en[u] : 0.0;
                     if (owner) se[gl * SPL + u] = eo[u];
                 }
-                __syncwarp(gmask);
             }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, !fin)) break;
         }
 
         // ---- epilogue (all documents of the warp together; w / part / se are those of the last trip) ----
@@ -264,8 +274,8 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
         }
 #pragma unroll
         for (int o = G >> 1; o > 0; o >>= 1) {
-            t1 += __shfl_xor_sync(gmask, t1, o);
-            sgd += __shfl_xor_sync(gmask, sgd, o);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            sgd += __shfl_xor_sync(0xffffffffu, sgd, o);
         }
         if (fini && gl == 0) {
             p.docterm[d] = t1 + p.lg_alpha - lgamma(p.alpha_sum + sgd);       // - lgamma(sum_k gamma_k), :197
@@ -274,14 +284,19 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
         if (fini) {
             // c_n phi_nk (:207): live columns from registers (minus the dead-topic value that k_dead_phi adds for
             // every column), and the row weights for k_dead_phi
+            // (all loads first: behind the reduce-adds they would each wait a full L2 round trip)
+            int cols[NC];
+            double ej[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) cols[j] = (j < nlive) ? rec[2 + j] : 0;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) ej[j] = se[j] - p.e_dead[cols[j]];
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 if (j < nlive) {
-                    const int col = rec[2 + j];
-                    const double ej = se[j] - p.e_dead[col];
 #pragma unroll
                     for (int i = 0; i < RPL; ++i)
-                        if (c[i] > 0.0) atomicAdd(p.phi_ss + (size_t)id[i] * KP + col, w[i] * bt[i][j] * ej);
+                        if (c[i] > 0.0) atomicAdd(p.phi_ss + (size_t)id[i] * KP + cols[j], w[i] * bt[i][j] * ej[j]);
                 }
             }
 #pragma unroll
@@ -295,15 +310,15 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
 #pragma unroll
         for (int i = 0; i < RPL; ++i) ws += w[i];
 #pragma unroll
-        for (int o = G >> 1; o > 0; o >>= 1) ws += __shfl_xor_sync(gmask, ws, o);
+        for (int o = G >> 1; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
         const bool full_pass = fini && !(ws <= p.chk_bound);
-        if (__any_sync(gmask, full_pass)) {
+        if (__any_sync(0xffffffffu, full_pass)) {
             for (int x = gl; x < 32; x += G) lm[x] = 0u;
-            __syncwarp(gmask);
+            __syncwarp();
 #pragma unroll
             for (int u = 0; u < SPL; ++u)
                 if (ov[u]) atomicOr(lm + (ck[u] >> 5), 1u << (ck[u] & 31));
-            __syncwarp(gmask);
+            __syncwarp();
             bool came_back = false;
             for (int k0 = 0; k0 < K; k0 += G) {
                 const int k = k0 + gl;
@@ -313,17 +328,17 @@ __global__ void __launch_bounds__(128, 3) estep_narrow(const NParams p) {
 #pragma unroll
                 for (int i = 0; i < RPL; ++i) {
                     for (int q = 0; q < G; ++q) {
-                        const double wq = __shfl_sync(gmask, w[i], g * G + q);
-                        const int idq = __shfl_sync(gmask, id[i], g * G + q);
-                        if (dead && q + G * i < n) {
+                        const double wq = __shfl_sync(0xffffffffu, w[i], g * G + q);
+                        const int idq = __shfl_sync(0xffffffffu, id[i], g * G + q);
+                        if (full_pass && dead && q + G * i < n) {
                             const double bv = p.Bt[(size_t)idq * KP + k];
                             sk = fma(wq, bv, sk);
                         }
                     }
                 }
-                if (dead && fma(ed, sk, p.alpha[k]) != p.alpha[k]) came_back = true;
+                if (full_pass && dead && fma(ed, sk, p.alpha[k]) != p.alpha[k]) came_back = true;
             }
-            if (__any_sync(gmask, came_back) && gl == 0 && p.revived) atomicAdd(p.revived, 1);
+            if ((__ballot_sync(0xffffffffu, came_back) & gmask) && gl == 0 && p.revived) atomicAdd(p.revived, 1);
         }
         __syncwarp();
     }

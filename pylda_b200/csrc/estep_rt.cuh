@@ -322,7 +322,7 @@ __device__ __forceinline__ int rt_trips(const EParams& p, double* es2, double* s
                         // few enough topics alive: park the document for the narrow stages (estep_narrow.cuh)
                         const unsigned lvb = __ballot_sync(0xffffffffu, valid && gnc != alt);
                         const int nl2 = __popc(lvb);
-                        if (nl2 >= 1 && nl2 <= (n <= 96 ? p.park_nc : 8)) {
+                        if (nl2 >= 1 && nl2 <= p.park_nc) {
                             int* rec = p.park_rec + (size_t)d * PARK_REC;
                             if ((lvb >> lane) & 1u) {
                                 const int rank = __popc(lvb & ((1u << lane) - 1u));

@@ -376,13 +376,13 @@ namespace pylda {
 template <int LK, int J, int RR>
 __device__ __forceinline__ void rows_accum_global(const double* __restrict__ Bt, int KP, int kl, const int* ridp,
                                                   const double* cntp, int gstride_rows, const double (&e)[2 * J],
-                                                  double (&s)[2 * J]) {
+                                                  double (&s)[2 * J], int npairs = J) {
     double b[RR][2 * J];
     double part[RR];
 #pragma unroll
     for (int i = 0; i < RR; ++i) {
         const double* rowp = Bt + (size_t)ridp[i * gstride_rows] * KP + 2 * kl;
-        part[i] = row_dot<LK, J>(rowp, e, b[i]);
+        part[i] = row_dot<LK, J>(rowp, e, b[i], npairs);
     }
 #pragma unroll
     for (int i = 0; i < RR; ++i) {
@@ -486,14 +486,29 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
 #pragma unroll
             for (int i = 0; i < 2 * J; ++i) s[i] = 0.0;
             {
+                // the warp's row groups gw, gw + W, ...: forwards on even trips, backwards on odd ones, so that the
+                // rows read last are read first again and the L1 cache (a fraction of the tile) is not swept
+                // cyclically -- every trip gets ~L1/tile of its rows from L1 instead of none
                 const int* ridp = rid + gw * LN + nl;
                 const double* cntp = cnt + gw * LN + nl;
-                int q = gw;
-                for (; q + W * (RR - 1) < NG; q += W * RR, ridp += RR * W * LN, cntp += RR * W * LN)
-                    rows_accum_global<LK, J, RR>(p.Bt, KP, kl, ridp, cntp, W * LN, e, s);
-                if (RR > 1) {
-                    for (; q < NG; q += W, ridp += W * LN, cntp += W * LN)
-                        rows_accum_global<LK, J, 1>(p.Bt, KP, kl, ridp, cntp, W * LN, e, s);
+                const int M = (NG - gw + W - 1) / W;
+                constexpr int GS = W * LN;
+                if (!(it & 1) || !p.compact) {
+                    int m = 0;
+                    for (; m + RR <= M; m += RR)
+                        rows_accum_global<LK, J, RR>(p.Bt, KP, kl, ridp + m * GS, cntp + m * GS, GS, e, s);
+                    if (RR > 1) {
+                        for (; m < M; ++m)
+                            rows_accum_global<LK, J, 1>(p.Bt, KP, kl, ridp + m * GS, cntp + m * GS, GS, e, s);
+                    }
+                } else {
+                    int m = M;
+                    for (; m >= RR; m -= RR)
+                        rows_accum_global<LK, J, RR>(p.Bt, KP, kl, ridp + (m - RR) * GS, cntp + (m - RR) * GS, GS, e, s);
+                    if (RR > 1) {
+                        for (; m > 0; --m)
+                            rows_accum_global<LK, J, 1>(p.Bt, KP, kl, ridp + (m - 1) * GS, cntp + (m - 1) * GS, GS, e, s);
+                    }
                 }
             }
 #pragma unroll

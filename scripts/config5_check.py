@@ -15,6 +15,14 @@ ctx = native.EStepContext(0)
 ctx.set_corpus(0, row_ptr, ids, cts)
 t = time.time()
 ctx.set_model(eta, alpha)
+for kern in os.environ.get("C5_KERNELS", "").split(","):      # tuning aid: time other long-document kernels first
+    if kern:
+        os.environ["PYLDA_KERNEL"] = kern
+        for _ in range(2):
+            s2 = ctx.estep_resident(0, 50, 1e-6)
+        print("PYLDA_KERNEL=%s: kernel %.1f ms, %.0f docs/s, streamed %d" % (kern, s2["kernel_ms"], D / (s2["total_ms"] * 1e-3), s2["docs_streamed"]), flush=True)
+        del os.environ["PYLDA_KERNEL"]
+st = ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
 st = ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
 print("E-step %.1f ms kernel, %.1f ms prep, %.1f ms post; wall incl. H2D %.1fs" % (st["kernel_ms"], st["prep_ms"], st["post_ms"], time.time() - t), flush=True)
 res = ctx.get_results(0, gamma=True, phi=True, alpha_ss=True, iters=True)
