@@ -121,7 +121,7 @@ struct pylda_ctx {
     double* partial = nullptr;   // reduction scratch
     size_t partial_cap = 0;
     int* counters = nullptr;     // class queue heads
-    int* park_ctr = nullptr;     // narrow stages: list lengths [0..8) and queue heads [8..16)
+    int* park_ctr = nullptr;     // narrow stages: list lengths [0..16) and queue heads [16..32)
     double* e_dead = nullptr;    // (K,) exp(psi(alpha_k))
     double* wsum = nullptr;      // (V,) row weights of the documents finished by the narrow stages
     bool model_set = false;
@@ -542,7 +542,7 @@ int launch_streaming(pylda_ctx* ctx, Corpus& cp, long long nd, int LK, int J, in
 
 // second-generation streaming kernel for documents [lo, hi) of the sorted order (all with n <= nmax)
 int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int nmax, int LK, int J, int max_iter,
-                   double tol, pylda_stats* st, int counter_slot, int* launched) {
+                   double tol, pylda_stats* st, int counter_slot, int* launched, int park_nc) {
     *launched = 0;
     const void* fn = estep_stream_lookup(LK, J);
     if (!fn) return 0;
@@ -575,6 +575,9 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
         const char* z = getenv("PYLDA_ZIGZAG");                 // alternate the row order trip by trip (L1 reuse)
         p.compact = !(z && !strcmp(z, "0"));
     }
+    p.park_nc = park_nc;
+    p.park_rec = cp.park_rec; p.park_gam = cp.park_gam; p.park_lists = cp.park_lists;
+    p.park_counts = ctx->park_ctr; p.park_cap = (int)cp.D;
     p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt; p.off_rid = gl.off_rid;
     void* args[] = {&p};
     CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)gl.bytes, ctx->stream));
@@ -615,14 +618,14 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
     k_e_dead<<<(ctx->K + 127) / 128, 128, 0, ctx->stream>>>(ctx->alpha, ctx->K, ctx->e_dead);
     CK(cudaMemsetAsync(ctx->wsum, 0, (size_t)ctx->V * sizeof(double), ctx->stream));
     st->n_launches++;
-    // launch order: the 16-column lists (0, 1, 2, 7) feed the 8-column ones (3..6)
-    static const int order[PARK_LISTS] = {0, 1, 2, 7, 3, 4, 5, 6};
-    static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8, 16};
-    static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32, 32};
-    static const int RPLs[PARK_LISTS] = {3, 3, 3, 6, 6, 6, 6, 6};
+    // launch order: the 32-column list (8) feeds the 16-column ones (0, 1, 2, 7), which feed the 8-column ones (3..6)
+    static const int order[PARK_LISTS] = {8, 0, 1, 2, 7, 3, 4, 5, 6};
+    static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8, 16, 32};
+    static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32, 32, 32};
+    static const int RPLs[PARK_LISTS] = {3, 3, 3, 6, 6, 6, 6, 6, 3};
     for (int oi = 0; oi < PARK_LISTS; ++oi) {
         const int li = order[oi];
-        if (NCs[li] > pc.nc) continue;
+        if (NCs[li] > 8 && pc.nc < 16) continue;        // PYLDA_PARK=8: the 8-column stage only
         const int NC = NCs[li], G = Gs[li];
         // CTAs per SM the kernel is compiled for: 2 (255 registers, no spills) or 3 (168 registers, tuning aid)
         int minb = 2;
@@ -644,7 +647,7 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.wsum = ctx->wsum; p.docterm = cp.docterm; p.iters = cp.iters;
         p.K = ctx->K; p.KP = ctx->KP; p.max_iter = max_iter; p.tol = tol;
         p.lg_alpha = ctx->lg_alpha; p.alpha_sum = ctx->alpha_sum;
-        p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 8 + li;
+        p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 16 + li;
         p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
         p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
         void* args[] = {&p};
@@ -675,10 +678,10 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     const char* kv = getenv("PYLDA_KERNEL");
     const bool use_rt = !(kv && !strcmp(kv, "v2"));
     int R_hy = 0;
-    // The hybrid register / shared-memory cluster kernel keeps whole long documents on chip.  It is the default
-    // where a term row is so wide (K > 256) that no single-CTA class exists and everything would stream from L2;
-    // at K ~ 100 the streaming kernel is still faster (profiles/r2b_*), PYLDA_KERNEL=hybrid selects it anyway.
-    const bool want_hy = kv ? !strcmp(kv, "hybrid") : (K > 256);
+    // The hybrid register / shared-memory cluster kernel keeps whole long documents on chip (PYLDA_KERNEL=hybrid).
+    // Measured (profiles/r2b_*): its per-trip serial phase (owner sums, exp(psi), cluster exchange) costs what the
+    // residency saves -- 73 ms vs 64 ms for the long documents of the headline config -- so streaming stays the default.
+    const bool want_hy = kv && !strcmp(kv, "hybrid");
     const void* fn_hy = want_hy ? estep_hy_lookup(LK, J, &R_hy) : nullptr;
 
     // Candidate classes, each with a row capacity; a document goes to the class with the smallest
@@ -725,7 +728,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         return std::partition_point(ns.begin(), ns.end(), [&](int n) { return n > limit; }) - ns.begin();
     };
     CK(cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(int), ctx->stream));
-    CK(cudaMemsetAsync(ctx->park_ctr, 0, 16 * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->park_ctr, 0, PARK_CTRS * sizeof(int), ctx->stream));
     const ParkCfg pc = park_config(ctx);
     for (int i = 0; i < NC; ++i) cls[i].lo = first_leq(cls[i].cap);
     for (int i = 0; i < NC; ++i) cls[i].hi = (i + 1 < NC) ? cls[i + 1].lo : D;
@@ -859,7 +862,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             if (s2_lo < nstream) {
                 int launched = 0;
                 timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream - s2_lo, ns[s2_lo]);
-                if (launch_stream2(ctx, cp, s2_lo, nstream, ns[s2_lo], LK, J, max_iter, tol, st, 15, &launched)) return 1;
+                if (launch_stream2(ctx, cp, s2_lo, nstream, ns[s2_lo], LK, J, max_iter, tol, st, 15, &launched, pc.nc)) return 1;
                 timer.end(ctx->stream);
                 if (!launched) s2_lo = nstream;
             }
@@ -984,8 +987,8 @@ int pylda_create(pylda_ctx** out, int device) {
     cudaMemset(ctx->scal, 0, 8 * sizeof(double));
     cudaMalloc((void**)&ctx->counters, 16 * sizeof(int));
     cudaMemset(ctx->counters, 0, 16 * sizeof(int));
-    cudaMalloc((void**)&ctx->park_ctr, 16 * sizeof(int));
-    cudaMemset(ctx->park_ctr, 0, 16 * sizeof(int));
+    cudaMalloc((void**)&ctx->park_ctr, PARK_CTRS * sizeof(int));
+    cudaMemset(ctx->park_ctr, 0, PARK_CTRS * sizeof(int));
     *out = ctx;
     return 0;
 }
@@ -1219,11 +1222,11 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     st.docs_at_cap = (int64_t)llround(ctx->last_scal[4]);
     st.row_trips = ctx->last_scal[5];
     {
-        int rv = 0, pk[8] = {0};
+        int rv = 0, pk[16] = {0};
         cudaMemcpy(&rv, ctx->counters + 14, sizeof(int), cudaMemcpyDeviceToHost);
         cudaMemcpy(pk, ctx->park_ctr, sizeof pk, cudaMemcpyDeviceToHost);
         st.revived_docs = rv;
-        st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2] + pk[7];
+        st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2] + pk[7] + pk[8];
         st.docs_narrow = (long long)pk[3] + pk[4] + pk[5] + pk[6];
     }
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;

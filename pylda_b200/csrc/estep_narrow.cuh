@@ -25,13 +25,16 @@
 
 namespace pylda {
 
-constexpr int PARK_REC = 20;    // ints per parked document: [0] trips done, [1] live topics, [2..18) their columns
-constexpr int PARK_GAM = 16;    // doubles per parked document: gamma of the live topics (same order)
-constexpr int PARK_LISTS = 8;   // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96) [0..2] and G = 32 with 6 rows per lane
-                                // (n <= 192) [7]; 8-column stage: G = 4, 8, 16, 32 (n <= 24, 48, 96, 192) [3..6]
+constexpr int PARK_REC = 36;    // ints per parked document: [0] trips done, [1] live topics, [2..34) their columns
+constexpr int PARK_GAM = 32;    // doubles per parked document: gamma of the live topics (same order)
+constexpr int PARK_LISTS = 9;   // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96) [0..2] and G = 32 with 6 rows per lane
+                                // (n <= 192) [7]; 8-column stage: G = 4, 8, 16, 32 (n <= 24, 48, 96, 192) [3..6];
+                                // 32-column stage: G = 32 (n <= 96) [8], fed by the kernels without a compact stage
+constexpr int PARK_CTRS = 32;   // ints: list lengths [0, 16) and queue heads [16, 32)
 
 // list a parked document joins: by stage (live topics) and length
 __device__ __forceinline__ int park_list_index(int nlive, int n) {
+    if (nlive > 16) return 8;
     if (nlive > 8) return n <= 24 ? 0 : n <= 48 ? 1 : n <= 96 ? 2 : 7;
     return n <= 24 ? 3 : n <= 48 ? 4 : n <= 96 ? 5 : 6;
 }
@@ -206,8 +209,8 @@ __global__ void __launch_bounds__(128, MINB) estep_narrow(const NParams p) {
                 ++it;
                 fin = dd <= tolK || it >= p.max_iter;                     // :189-190 / :174
             }
-            if (NC == 16) {
-                // hand-over to the 8-column stage once at most 8 topics are alive
+            if (NC > 8) {
+                // hand-over to the next narrower stage once at most NC / 2 topics are alive
                 unsigned bal[SPL];
                 int nl = 0;
 #pragma unroll
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(128, MINB) estep_narrow(const NParams p) {
                     bal[u] = __ballot_sync(0xffffffffu, lv[u]) & gmask;
                     nl += __popc(bal[u]);
                 }
-                if (running && !fin && nl <= 8) {
+                if (running && !fin && nl <= NC / 2) {
                     int* wrec = p.rec + (size_t)d * PARK_REC;
                     const unsigned below = gmask & ((1u << lane) - 1u);
                     int rank = 0;

@@ -18,6 +18,7 @@
 //   * the queue index of the next document is prefetched.
 #pragma once
 #include "estep_kernel.cuh"
+#include "estep_narrow.cuh"
 
 namespace pylda {
 
@@ -475,6 +476,9 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         double e[2 * J];
         int it = 0;
         const double tolK = p.tol * (double)K;
+        // hand-over threshold of this document: 32 live topics for n <= 96, 16 for n <= 192, never above
+        const int park_thr = (p.park_nc >= 16 && n <= 96) ? 32 : (p.park_nc > 0 && n <= 192) ? p.park_nc : 0;
+        bool parked = false;
         while (true) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -561,9 +565,55 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
 #pragma unroll
             for (int w = 0; w < W; ++w) dsum += red[w];
             if (dsum <= tolK || it >= p.max_iter) break;                  // :189-190 / :174
+            if (park_thr > 0) {
+                // Few enough topics alive (gamma_k != alpha_k): the narrow stages (estep_narrow.cuh) finish the
+                // document.  This kernel has no compact stage of its own, so it hands over at 32 live topics already.
+                unsigned bal[U];
+                int mine = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int k = gt + GT * u;
+                    bal[u] = __ballot_sync(0xffffffffu, k < K && gn[u] != alr[u]);
+                    mine += __popc(bal[u]);
+                }
+                if (lane == 0) red[W + gw] = (double)mine;      // (red[W ..) belongs to the ELBO exchange of the final pass)
+                __syncthreads();
+                int nlive = 0, rank = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const int c = (int)red[W + w];
+                    nlive += c;
+                    if (w < gw) rank += c;
+                }
+                if (nlive >= 1 && nlive <= park_thr) {
+                    int* rec = p.park_rec + (size_t)d * PARK_REC;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = gt + GT * u;
+                        if (k < K) p.gamma[(size_t)d * K + k] = gamr[u];       // final for every dead topic
+                        if ((bal[u] >> lane) & 1u) {
+                            const int slot = rank + __popc(bal[u] & ((1u << lane) - 1u));
+                            rec[2 + slot] = k;
+                            p.park_gam[(size_t)d * PARK_GAM + slot] = gamr[u];
+                        }
+                        rank += __popc(bal[u]);
+                    }
+                    if (gt == 0) {
+                        rec[0] = it;
+                        rec[1] = nlive;
+                        const int li = park_list_index(nlive, n);
+                        const int slot = atomicAdd(p.park_counts + li, 1);
+                        p.park_lists[(size_t)li * p.park_cap + slot] = d;
+                    }
+                    parked = true;
+                    break;
+                }
+                __syncthreads();                                 // red[W ..] is reused next trip
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) er[u] = en[u];
         }
+        if (parked) continue;
 
         // ---- final pass: phi from the LAST e, scattered with red.global.add.f64 -----------------
         double lacc = 0.0;
