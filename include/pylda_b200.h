@@ -55,7 +55,8 @@ typedef struct pylda_stats {
     int64_t docs_streamed;     /* documents whose tile was re-streamed from L2/HBM            */
     double  row_trips;         /* sum_d n_d * iters_d: 4*KP*row_trips = fp64 flops of the mat-vecs */
     int64_t revived_docs;      /* documents in which a topic eliminated as dead (gamma_k == alpha_k) would have
-                                  come back; must be 0 (then the elimination changed nothing), local to the rank */
+                                  come back (summed over ranks).  0 in every corpus seen so far; when it is not, the
+                                  library has already redone the E-step at full width and the results are those */
     int64_t docs_narrow_wide;     /* documents handed to the 16-column narrow stage (at most 16 topics alive)     */
     int64_t docs_narrow;      /* documents that went through the 8-column narrow stage (at most 8 alive)      */
 } pylda_stats;

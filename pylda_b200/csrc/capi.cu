@@ -127,6 +127,9 @@ struct pylda_ctx {
     bool model_set = false;
     bool phi_KV_valid = false;
     bool have_alpha_ss = false;
+    bool force_full = false;     // redo of an E-step in which an eliminated topic came back: no elimination, no hand-over
+    int phi_slot = -1;           // which corpus slot / branch produced the statistics in `phi`
+    bool phi_heldout = false;
     double last_scal[8] = {0};
     // comm
     ncclComm_t comm = nullptr;
@@ -610,7 +613,7 @@ ParkCfg park_config(const pylda_ctx* ctx) {
     c.chk_bound = ed > 0.0 ? ctx->alpha_min * ldexp(1.0, -54) / ed : HUGE_VAL;
     if (!(c.chk_bound >= 1e3)) c.nc = 0;
     const char* ce = getenv("PYLDA_COMPACT");
-    if (ce && !strcmp(ce, "0")) c.nc = 0;
+    if ((ce && !strcmp(ce, "0")) || ctx->force_full) c.nc = 0;
     return c;
 }
 
@@ -912,7 +915,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         p.W = W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = G * gl.bytes;
         {
             const char* ce = getenv("PYLDA_COMPACT");
-            p.compact = !(ce && !strcmp(ce, "0"));
+            p.compact = !(ce && !strcmp(ce, "0")) && !ctx->force_full;
             p.revived = ctx->counters + 14;
             p.park_nc = (c.kind == 1) ? pc.nc : 0;
             p.park_rec = cp.park_rec; p.park_gam = cp.park_gam; p.park_lists = cp.park_lists;
@@ -1223,7 +1226,13 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     st.row_trips = ctx->last_scal[5];
     {
         int rv = 0, pk[16] = {0};
+        if (ctx->comm) {      // every rank must take the same decision about the full-width redo below
+            const int rc = g_nccl.AllReduce(ctx->counters + 14, ctx->counters + 14, 1, /*ncclInt32*/ 2, kNcclSum, ctx->comm, ctx->stream);
+            if (rc) return fail(ctx, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         cudaMemcpy(&rv, ctx->counters + 14, sizeof(int), cudaMemcpyDeviceToHost);
+        if (getenv("PYLDA_TEST_FORCE_REDO") && !ctx->force_full) rv += 1;     // test hook: exercises the redo path
         cudaMemcpy(pk, ctx->park_ctr, sizeof pk, cudaMemcpyDeviceToHost);
         st.revived_docs = rv;
         st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2] + pk[7] + pk[8];
@@ -1231,6 +1240,20 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     }
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;
     st.algo_total_bytes = st.algo_read_bytes + 8.0 * (double)cp.D * K + 8.0 * (double)cp.nnz * K;
+    ctx->phi_slot = slot;
+    ctx->phi_heldout = heldout != 0;
+    if (st.revived_docs > 0 && !ctx->force_full) {
+        // The elimination of dead topics (gamma_k == alpha_k) assumes they stay dead; every kernel checks it per
+        // document.  A violation has never been observed, but if one is, the results above are not the
+        // reference's: redo the whole E-step with every trip at full width (a collective decision under NCCL:
+        // the counter is local, so the ranks agree on it first).
+        const int64_t seen = st.revived_docs;
+        ctx->force_full = true;
+        const int rc = estep_resident_impl(ctx, slot, max_iter, tol, heldout, want_alpha_ss, &st, gamma_host_alias);
+        ctx->force_full = false;
+        if (rc) return 1;
+        st.revived_docs = seen;
+    }
     if (stats) *stats = st;
     return 0;
 }
@@ -1293,6 +1316,9 @@ int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, do
     if (!ctx) return 1;
     if (!ctx->model_set) return fail(ctx, "pylda_mstep_resident: no model on the device");
     if (!ctx->corp[0].has_results) return fail(ctx, "pylda_mstep_resident: run the training E-step first");
+    if (ctx->phi_slot != 0 || ctx->phi_heldout)
+        return fail(ctx, "pylda_mstep_resident: the statistics on the device come from a held-out E-step (slot %d); "
+                         "run the training E-step (slot 0) again first", ctx->phi_slot);
     if (!(alpha_beta > 0.0)) return fail(ctx, "pylda_mstep_resident: alpha_beta must be > 0");
     CK(cudaSetDevice(ctx->device));
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;

@@ -114,10 +114,12 @@ def main(argv=None):
     lda_inferencer._initialize(train_docs, vocab, number_of_topics, alpha_alpha, alpha_beta)       # :194
     for _ in range(training_iterations):                                                           # :196-201
         lda_inferencer.learning()
-        if lda_inferencer._counter % snapshot_interval == 0 and rank == 0:
-            # multi-process: beta is global; exp_gamma holds rank 0's document shard
-            lda_inferencer.export_beta(output_directory + "exp_beta-" + str(lda_inferencer._counter))
-            lda_inferencer.export_gamma(output_directory + "exp_gamma-" + str(lda_inferencer._counter))
+        if lda_inferencer._counter % snapshot_interval == 0:
+            lda_inferencer.materialize()       # multi-process: gathers the gamma shards of all ranks (collective)
+            if rank == 0:
+                lda_inferencer.export_beta(output_directory + "exp_beta-" + str(lda_inferencer._counter))
+                lda_inferencer.export_gamma(output_directory + "exp_gamma-" + str(lda_inferencer._counter))
+    lda_inferencer.materialize()
     if rank == 0:
         model_snapshot_path = os.path.join(output_directory, "model-" + str(lda_inferencer._counter))
         with open(model_snapshot_path, "wb") as f:                                                 # :203-204

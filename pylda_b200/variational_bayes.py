@@ -65,7 +65,10 @@ class VariationalBayes(Inferencer):
     def _gamma(self):
         d = self.__dict__
         if d.get("_gamma_stale") and d.get("_native") is not None:
-            d["_gamma_host"] = d["_native"].get_results(0, gamma=True, phi=False)["gamma"]
+            rows = d["_native"].get_results(0, gamma=True, phi=False)["gamma"]
+            lo, hi = d.get("_gamma_rows", (0, rows.shape[0]))
+            # multi-process: a collective -- every rank must read _gamma at the same point (materialize())
+            d["_gamma_host"] = self._gather_rows(rows, lo, hi, self._number_of_documents)
             d["_gamma_stale"] = False
         return d.get("_gamma_host")
 
@@ -82,6 +85,7 @@ class VariationalBayes(Inferencer):
         state["_train_uploaded"] = False
         state["_alpha_ss_device"] = None
         state["_model_on_device"] = False
+        state.pop("_last_parsed_csr", None)                    # (attribute of older versions)
         return state
 
     def _context(self):
@@ -89,7 +93,8 @@ class VariationalBayes(Inferencer):
         LOCAL_RANK in the environment, e.g. by torchrun) the ranks are joined with NCCL: every rank
         parses the same corpus, runs the E-step on its own nnz-balanced shard of documents, and the
         library all-reduces the K x V statistics, the ELBO scalars and the alpha statistics.
-        self._gamma then holds the rows of the local shard only (self._gamma_rows = (lo, hi))."""
+        The device keeps the gamma rows of the local shard (self._gamma_rows = (lo, hi)); self._gamma gathers
+        all D rows over NCCL when it is read."""
         if self._native is None:
             rank, size, local = distributed.world()
             self._native = native.EStepContext(local)
@@ -125,13 +130,15 @@ class VariationalBayes(Inferencer):
     def _initialize(self, corpus, vocab, number_of_topics, alpha_alpha, alpha_beta):
         # :82-95
         Inferencer._initialize(self, vocab, number_of_topics, alpha_alpha, alpha_beta)
-        self._parsed_corpus = self.parse_data(corpus)
+        self._parsed_corpus, csr = self._parse(corpus)
         self._number_of_documents = len(self._parsed_corpus[0])
         self._gamma = numpy.zeros((self._number_of_documents, self._number_of_topics)) \
             + self._alpha_alpha[numpy.newaxis, :] + 1.0 * self._number_of_types / self._number_of_topics
         # the only random draw that affects VB results (:95); same global-RNG call as the reference
         self._eta = numpy.random.gamma(100., 1. / 100., (self._number_of_topics, self._number_of_types))
-        csr = self.__dict__.pop("_last_parsed_csr", None)      # the native parser already produced the CSR
+        # (the native parser already produced the CSR of exactly this corpus; checked, never trusted blindly)
+        if csr is not None and len(csr[0]) - 1 != self._number_of_documents:
+            csr = None
         self._train_csr = csr if csr is not None else pack_parsed_corpus(self._parsed_corpus)
         self._train_uploaded = False
         rank, size, _ = distributed.world()
@@ -144,8 +151,14 @@ class VariationalBayes(Inferencer):
     def parse_data(self, corpus):
         # :98-130 -- per document: unique in-vocabulary type ids (first-seen order) and counts;
         # documents with no in-vocabulary token are dropped with a warning.
-        # Fast path: the native parser of the C ABI (pylda_parse_corpus, multi-threaded host code, same
-        # semantics bit for bit); the loop below remains for non-ASCII text and as its specification.
+        return self._parse(corpus)[0]
+
+    def _parse(self, corpus):
+        """parse_data plus the CSR form of the same corpus when the native parser produced it (else None).
+        Nothing is kept on the object: a CSR left over from an earlier call can never be mistaken for
+        the corpus of a later one.
+        Fast path: the native parser of the C ABI (pylda_parse_corpus, multi-threaded host code, same
+        semantics bit for bit); the loop below remains for non-ASCII text and as its specification."""
         if os.environ.get("PYLDA_NATIVE_PARSE", "1") != "0" and isinstance(corpus, (list, tuple)):
             parsed = native.parse_corpus(corpus, self._index_to_type)
             if parsed is not None:
@@ -159,8 +172,7 @@ class VariationalBayes(Inferencer):
                 for done in range(10000, len(word_ids) + 1, 10000):
                     print("successfully parse %d documents..." % done)
                 print("successfully parse %d documents..." % len(word_ids))
-                self._last_parsed_csr = (row_ptr, ids, cts)
-                return (word_ids, word_cts)
+                return (word_ids, word_cts), (row_ptr, ids, cts)
         doc_count = 0
         word_ids, word_cts = [], []
         lookup = self._type_to_index
@@ -181,23 +193,29 @@ class VariationalBayes(Inferencer):
                 print("successfully parse %d documents..." % doc_count)
         assert len(word_ids) == len(word_cts)
         print("successfully parse %d documents..." % doc_count)
-        return (word_ids, word_cts)
+        return (word_ids, word_cts), None
 
     def e_step(self, parsed_corpus=None, local_parameter_iteration=50, local_parameter_converge_threshold=1e-6):
         """:132-216.  Train branch (parsed_corpus is None): sets self._gamma and returns
         (document_log_likelihood, phi_sufficient_statistics (K,V)).  Held-out branch: returns
         (words_log_likelihood, gamma_values) and leaves self._gamma untouched."""
+        return self._e_step_impl(parsed_corpus, local_parameter_iteration, local_parameter_converge_threshold, None)
+
+    def _e_step_impl(self, parsed_corpus, local_parameter_iteration, local_parameter_converge_threshold, csr):
         ctx = self._context()
         heldout = parsed_corpus is not None
         multi = self._world > 1
         if heldout:
             word_ids, word_cts = parsed_corpus[0], parsed_corpus[1]
             assert len(word_ids) == len(word_cts)
-            lo, hi, shard = self._shard(pack_parsed_corpus((word_ids, word_cts)))
+            if csr is None or len(csr[0]) - 1 != len(word_ids):
+                csr = pack_parsed_corpus((word_ids, word_cts))
+            lo, hi, shard = self._shard(csr)
             ctx.set_corpus(1, *shard)
             slot, number_of_documents = 1, len(word_ids)
         else:
             self._upload_train(ctx)
+            lo, hi = self._gamma_rows
             slot, number_of_documents = 0, len(self._parsed_corpus[0])
         # the reference visits documents in numpy.random.permutation order (:159); the order only
         # changes fp summation order, but the draw keeps the global RNG stream in step with it
@@ -207,11 +225,22 @@ class VariationalBayes(Inferencer):
                         want_gamma=True, want_phi=not heldout, want_alpha_ss=multi and not heldout)
         self._last_estep_stats = out["stats"]
         self.__dict__["_model_on_device"] = False      # pylda_estep re-uploads eta/alpha from the host
+        gamma = self._gather_rows(out["gamma"], lo, hi, number_of_documents)
         if not heldout:
-            self._gamma = out["gamma"]                 # multi-process: rows self._gamma_rows of the corpus
+            self._gamma = gamma                        # all D documents, as in the reference (:212)
             self._alpha_ss_device = out["alpha_ss"]    # summed over ranks by the library (None single-process)
             return out["doc_ll"], out["phi_ss"]
-        return out["words_ll"], out["gamma"]
+        return out["words_ll"], gamma
+
+    def _gather_rows(self, rows, lo, hi, number_of_documents):
+        """Multi-process: every rank holds the gamma rows [lo, hi) of its document shard; the reference's
+        callers (export_gamma :343-356, launch_test.py:95-97, the pickled model) expect all D rows.  The
+        shards are summed into a zero-padded D x K buffer over NCCL (a collective: every rank calls it)."""
+        if getattr(self, "_world", 1) <= 1:
+            return rows
+        full = numpy.zeros((number_of_documents, rows.shape[1]), dtype=numpy.float64)
+        full[lo:hi, :] = rows
+        return self._context().allreduce_sum(full)
 
     def m_step(self, phi_sufficient_statistics):
         # :218-235 -- topic terms from the OLD eta, then eta <- phi_ss + alpha_beta
@@ -288,9 +317,15 @@ class VariationalBayes(Inferencer):
 
     def inference(self, corpus):
         # :263-271
-        parsed_corpus = self.parse_data(corpus)
-        words_log_likelihood, corpus_gamma_values = self.e_step(parsed_corpus)
+        parsed_corpus, csr = self._parse(corpus)
+        words_log_likelihood, corpus_gamma_values = self._e_step_impl(parsed_corpus, 50, 1e-6, csr)
         return words_log_likelihood, corpus_gamma_values
+
+    def materialize(self):
+        """Bring eta and gamma (all D rows) to the host.  After resident EM iterations they live in HBM and
+        are fetched when read; in a multi-process run fetching gamma is a collective, so every rank calls
+        this before rank 0 exports or pickles the model (launch_train does)."""
+        return self._eta, self._gamma
 
     def optimize_hyperparameters(self, alpha_sufficient_statistics, hyper_parameter_iteration=100,
                                  hyper_parameter_decay_factor=0.9, hyper_parameter_maximum_decay=10,
@@ -346,7 +381,7 @@ class VariationalBayes(Inferencer):
         # :343-356
         exp_gamma = self._gamma / numpy.sum(self._gamma, axis=1)[:, numpy.newaxis]
         with open(exp_gamma_path, 'w') as output:
-            for document_index in range(exp_gamma.shape[0]):     # all documents; the local shard when multi-process
+            for document_index in range(exp_gamma.shape[0]):
                 fields = []
                 for rank, topic_index in enumerate(reversed(numpy.argsort(exp_gamma[document_index, :])), 1):
                     fields.append("%d:%g" % (topic_index, exp_gamma[document_index, topic_index]))

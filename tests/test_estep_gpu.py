@@ -371,3 +371,19 @@ def test_narrow_stages_off_when_alpha_is_large(ctx):
     ctx.set_corpus(0, row_ptr, ids, cts)
     out = ctx.estep(0, synthetic.initial_eta(K, V, 0), numpy.full(K, 0.05), 50, 1e-6)
     assert out["stats"]["docs_narrow"] == 0 and out["stats"]["docs_narrow_wide"] == 0
+
+
+def test_full_width_redo_when_an_eliminated_topic_comes_back(ctx, monkeypatch):
+    """The kernels verify per document that every topic eliminated as dead stays dead (stats.revived_docs).
+    If that ever fails the library redoes the E-step with the elimination and the narrow stages off; the
+    test hook forces that path and the results must be the plain full-width ones."""
+    g = load_golden("zipf48_k100")
+    ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
+    plain = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6)
+    assert plain["stats"]["revived_docs"] == 0 and plain["stats"]["docs_narrow"] > 0
+    monkeypatch.setenv("PYLDA_TEST_FORCE_REDO", "1")
+    redo = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6)
+    monkeypatch.delenv("PYLDA_TEST_FORCE_REDO")
+    assert redo["stats"]["revived_docs"] == 1 and redo["stats"]["docs_narrow"] == 0
+    _check(dict(redo, stats=None), g["gamma"], g["phi_ss"], g["doc_ll"], "redo")
+    assert max_rel(redo["gamma"], plain["gamma"]) <= 1e-11
