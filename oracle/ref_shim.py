@@ -3,9 +3,10 @@
 Loads /root/reference/{inferencer,variational_bayes}.py (Python 2 sources) into
 Python 3 modules at import time through a line-level source shim.  Nothing from
 the reference is copied into this repository: the text is read where it lies,
-rewritten in memory and exec'd.  This only works where /root/reference exists
-(the build container); the GPU box has no reference, so only
-oracle/make_golden.py and the "not gpu" pin tests may call this.
+rewritten in memory and exec'd.  The sources are searched in $PYLDA_REF, baseline/_ref/
+(git-ignored staging copy made by stage(), the only way they reach the GPU box) and
+/root/reference.  Callers: oracle/make_golden.py, the "not gpu" pin tests and the
+`--impl reference` arm of bench.py.
 
 Shim steps:
   1. stub `nltk` (imported at variational_bayes.py:10 / inferencer.py:8, unused on the path)
@@ -18,11 +19,40 @@ import re
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PYLDA_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# where the reference sources are looked for, in this order: $PYLDA_REF, baseline/_ref (git-ignored staging
+# area that travels to the GPU box with the gpurun snapshot; filled by stage()), /root/reference
+SEARCH = [p for p in (os.environ.get("PYLDA_REF"), os.path.join(_HERE, "..", "baseline", "_ref"), "/root/reference") if p]
+
+
+def _find_root():
+    for root in SEARCH:
+        if os.path.isfile(os.path.join(root, "variational_bayes.py")) and os.path.isfile(os.path.join(root, "inferencer.py")):
+            return os.path.abspath(root)
+    return None
+
+
+REFERENCE_ROOT = _find_root() or "/root/reference"
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "variational_bayes.py"))
+    return _find_root() is not None
+
+
+def stage(dst=None):
+    """Copy the two reference files of the path (inferencer.py, variational_bayes.py) from /root/reference into
+    baseline/_ref/ -- git-ignored, never part of the repository's history, but shipped with the gpurun
+    snapshot -- so that `bench.py --impl reference` can time the UNMODIFIED reference on the GPU box's host
+    cores.  Returns the directory, or None when /root/reference is not there."""
+    import shutil
+    src = "/root/reference"
+    if not os.path.isfile(os.path.join(src, "variational_bayes.py")):
+        return None
+    dst = dst or os.path.join(_HERE, "..", "baseline", "_ref")
+    os.makedirs(dst, exist_ok=True)
+    for name in ("inferencer.py", "variational_bayes.py"):
+        shutil.copyfile(os.path.join(src, name), os.path.join(dst, name))
+    return os.path.abspath(dst)
 
 
 _PRINT = re.compile(r"^(\s*)print\s+(?!\()(.*?);?\s*$")
@@ -46,8 +76,9 @@ def _to_py3(text):
 
 def load():
     """Return (inferencer_module, variational_bayes_module) built from the reference sources."""
-    if not available():
-        raise RuntimeError("reference sources not found under %s" % REFERENCE_ROOT)
+    root = _find_root()
+    if root is None:
+        raise RuntimeError("reference sources not found under any of %s" % SEARCH)
     import scipy
     import scipy.special
     if "nltk" not in sys.modules:
@@ -63,7 +94,7 @@ def load():
     saved = {n: sys.modules.get(n) for n in ("inferencer", "variational_bayes")}
     try:
         for name in ("inferencer", "variational_bayes"):
-            path = os.path.join(REFERENCE_ROOT, name + ".py")
+            path = os.path.join(root, name + ".py")
             with open(path, "r") as f:
                 src = _to_py3(f.read())
             mod = types.ModuleType(name)

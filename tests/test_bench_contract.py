@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -21,9 +23,24 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic" and d["scaling"] == "weak"
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert set(d["config"]) == {"workload", "state", "local_parameter_iteration", "converge_threshold", "scaling"}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    from oracle import ref_shim
+    # the unmodified reference when its sources are present ($PYLDA_REF, baseline/_ref, /root/reference), else the port
+    assert cb["kind"] == ("reference" if ref_shim.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert 30 <= d["run"]["mean_inner_trips"] <= 50
+
+
+def test_reference_arm_port_fallback():
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--docs", "6000", "--ref-docs-per-core", "10", "--ref-port"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([ln for ln in p.stdout.split("\n") if ln.strip()][0])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
