@@ -405,7 +405,7 @@ def run_product(args, cfg):
             shell.optimize_hyperparameters(alpha_ss)
             ctx.set_alpha(shell._alpha_alpha)
             em_wall.append(time.perf_counter() - t_em)
-        em_stats["ms"] = 1e3 * min(em_wall[:3])      # the 4th may include the eta copy-back
+        em_stats.setdefault("ms", 1e3 * min(em_wall[:3]))      # headline corpus only; the 4th may include the eta copy-back
         return eta_host, shell._alpha_alpha.copy()
 
     results = {}

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 7
+#define PYLDA_ABI_VERSION 8
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -121,6 +121,12 @@ int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, do
 int pylda_get_eta(pylda_ctx* ctx, double* eta_KxV);
 /* Replace alpha on the device (after the host Newton update, variational_bayes.py:277-324). */
 int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K);
+
+/* export_beta on the device (variational_bayes.py:326-341): for every topic the `top` most probable words under
+ * beta_kv = exp(E_log_eta[k,v] - logsumexp_v E_log_eta[k,:]) of the model currently on the device (pylda_set_model /
+ * after pylda_mstep_resident), most probable first.  idx_KxT: word (type) ids, prob_KxT: their probabilities, both
+ * K x top row-major host buffers.  Replaces K host argsorts over V entries and the K x V copy-back they need. */
+int pylda_top_words(pylda_ctx* ctx, int top, int32_t* idx_KxT, double* prob_KxT);
 
 /* compute_dirichlet_expectation (inferencer.py:15-18) for a (K,V) matrix on the device.
  * Exposed for parity tests of the device digamma. */

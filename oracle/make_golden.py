@@ -3,7 +3,7 @@ reference (variational_bayes.py / inferencer.py, loaded through oracle/ref_shim.
 
 Run in the build container only (needs /root/reference):
 
-    PYTHONHASHSEED=0 python oracle/make_golden.py [--trace]
+    PYTHONHASHSEED=0 python oracle/make_golden.py [--trace] [--nips-full [--only-nips-full]]
 
 Vocabulary ids come from set() iteration order (inferencer.py:63-65), so the script
 re-executes itself with PYTHONHASHSEED=0 when that is not set.  Fixtures hold the
@@ -109,29 +109,59 @@ def main():
     ap_test = _read_docs(os.path.join(ap, "test.dat"))
     ap_vocab = _read_vocab(os.path.join(ap, "voc.dat"))
 
-    # config 1 shape, first 200 docs, EM iteration 1 (random eta) + held-out branch
-    _run_case("ap200_k10", vb_mod, ap_train[:200], ap_vocab, 10, heldout_docs=ap_test[:40])
-    # same after 3 EM iterations (warm eta, asymmetric alpha, early-exit documents)
-    _run_case("ap200_k10_warm3", vb_mod, ap_train[:200], ap_vocab, 10, em_warm=3)
+    small = "--only-nips-full" not in sys.argv
+    if small:
+        # config 1 shape, first 200 docs, EM iteration 1 (random eta) + held-out branch
+        _run_case("ap200_k10", vb_mod, ap_train[:200], ap_vocab, 10, heldout_docs=ap_test[:40])
+        # same after 3 EM iterations (warm eta, asymmetric alpha, early-exit documents)
+        _run_case("ap200_k10_warm3", vb_mod, ap_train[:200], ap_vocab, 10, em_warm=3)
 
     # config 4 shape: nips.88-05 has doc.dat only
     nips = _extract("parsed/nips.88-05.tar.gz", "nips.88-05")
     nips_docs = _read_docs(os.path.join(nips, "doc.dat"))
     nips_vocab = _read_vocab(os.path.join(nips, "voc.dat"))
-    _run_case("nips24_k200", vb_mod, nips_docs[:24], nips_vocab, 200)
-
-    # synthetic, config 2 shape scaled down (K=50), rendered as text so it goes through
-    # the reference's own parse_data
     from pylda_b200 import synthetic
-    row_ptr, ids, cts = synthetic.synthetic_corpus(96, 1500, seed=1236, length="poisson", mean_len=100)
-    docs = synthetic.render_text(row_ptr, ids, cts)
-    vocab = ["w%d" % i for i in range(1500)]
-    _run_case("syn96_k50", vb_mod, docs, vocab, 50, em_warm=1)
-    # zipf lengths incl. one long document (config 3 shape scaled down, K=100)
-    row_ptr, ids, cts = synthetic.synthetic_corpus(48, 3000, seed=1237, length="zipf")
-    docs = synthetic.render_text(row_ptr, ids, cts)
-    vocab = ["w%d" % i for i in range(3000)]
-    _run_case("zipf48_k100", vb_mod, docs, vocab, 100)
+    if small:
+        _run_case("nips24_k200", vb_mod, nips_docs[:24], nips_vocab, 200)
+
+        # synthetic, config 2 shape scaled down (K=50), rendered as text so it goes through
+        # the reference's own parse_data
+        row_ptr, ids, cts = synthetic.synthetic_corpus(96, 1500, seed=1236, length="poisson", mean_len=100)
+        docs = synthetic.render_text(row_ptr, ids, cts)
+        vocab = ["w%d" % i for i in range(1500)]
+        _run_case("syn96_k50", vb_mod, docs, vocab, 50, em_warm=1)
+        # zipf lengths incl. one long document (config 3 shape scaled down, K=100)
+        row_ptr, ids, cts = synthetic.synthetic_corpus(48, 3000, seed=1237, length="zipf")
+        docs = synthetic.render_text(row_ptr, ids, cts)
+        vocab = ["w%d" % i for i in range(3000)]
+        _run_case("zipf48_k100", vb_mod, docs, vocab, 100)
+
+    if "--nips-full" in sys.argv:
+        # config 4 in full: nips.88-05 (doc.dat staged as the training corpus), K = 200, EM iteration 1.
+        # Kept small: the CSR as int16/uint16, gamma in full, phi_ss as every 16th occurring column plus its
+        # row and column sums, the ELBO, and the trip counts of the restatement (pinned to the reference here).
+        K = 200
+        numpy.random.seed(0)
+        lda = vb_mod.VariationalBayes()
+        lda._initialize(nips_docs, nips_vocab, K, 1.0 / K, 1.0 / len(set(nips_vocab)))
+        eta0 = lda._eta.copy()
+        from pylda_b200 import synthetic
+        assert numpy.array_equal(synthetic.initial_eta(K, lda._number_of_types, 0), eta0)
+        row_ptr, ids, cts = O.csr_from_parsed(*lda._parsed_corpus)
+        doc_ll, phi_ss = lda.e_step()
+        r = O.e_step(row_ptr, ids, cts, eta0, lda._alpha_alpha, return_iters=True)
+        rel = lambda a, b: float(numpy.max(numpy.abs(a - b) / numpy.maximum(numpy.abs(b), 1e-300)))
+        print("nips_full_k200 D=%d V=%d nnz=%d  oracle-vs-reference: gamma %.2e phi_ss(abs) %.2e doc_ll %.2e  mean trips %.1f" % (
+            len(row_ptr) - 1, lda._number_of_types, len(ids), rel(r["gamma"], lda._gamma),
+            float(numpy.max(numpy.abs(r["phi_ss"] - phi_ss))), abs(r["doc_ll"] - doc_ll) / abs(doc_ll), r["iters"].mean()))
+        assert ids.max() < 32768 and cts.max() < 65536
+        cols = numpy.unique(ids)[::16]
+        numpy.savez_compressed(os.path.join(GOLD, "nips_full_k200.npz"), K=K, V=lda._number_of_types, eta_seed=0,
+                               row_ptr=row_ptr.astype(numpy.int32), ids=ids.astype(numpy.int16), cts=cts.astype(numpy.uint16),
+                               alpha=lda._alpha_alpha.copy(), gamma=lda._gamma.copy(), phi_cols=cols,
+                               phi_ss_cols=phi_ss[:, cols], phi_rowsum=phi_ss.sum(axis=1), phi_colsum=phi_ss.sum(axis=0),
+                               doc_ll=numpy.float64(doc_ll), iters=r["iters"].astype(numpy.int8),
+                               eta_sha1=numpy.array(hashlib.sha1(eta0.tobytes()).hexdigest()))
 
     if "--trace" in sys.argv:
         # config 1 in full: AP, K=10, 20 VB iterations through the reference's learning()

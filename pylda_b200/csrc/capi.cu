@@ -17,9 +17,15 @@
 #include "estep_dispatch.h"
 #include "estep_kernel.cuh"
 #include "estep_narrow.cuh"
+#include "estep_sweep.cuh"
 #include "prep_kernels.cuh"
 
 using namespace pylda;
+
+namespace pylda {
+int device_top_words(const double* Elt, const double* lse, int K, int V, int KP, int top, int32_t* idx_out, double* prob_out,
+                     cudaStream_t s, std::string* err);
+}
 
 namespace {
 
@@ -124,6 +130,7 @@ struct pylda_ctx {
     int* park_ctr = nullptr;     // narrow stages: list lengths [0..16) and queue heads [16..32)
     double* e_dead = nullptr;    // (K,) exp(psi(alpha_k))
     double* wsum = nullptr;      // (V,) row weights of the documents finished by the narrow stages
+    float* Bt32 = nullptr;       // (V, KP) fp32 copy of Bt (precision sweep only, PYLDA_PRECISION)
     bool model_set = false;
     bool phi_KV_valid = false;
     bool have_alpha_ss = false;
@@ -172,8 +179,9 @@ void free_corpus(Corpus& c) {
 
 void free_model(pylda_ctx* c) {
     cudaFree(c->eta); cudaFree(c->alpha); cudaFree(c->Elt); cudaFree(c->Bt); cudaFree(c->mw);
-    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss); cudaFree(c->e_dead); cudaFree(c->wsum);
+    cudaFree(c->phi); cudaFree(c->phi_KV); cudaFree(c->kbuf); cudaFree(c->alpha_ss); cudaFree(c->e_dead); cudaFree(c->wsum); cudaFree(c->Bt32);
     c->eta = c->alpha = c->Elt = c->Bt = c->mw = c->phi = c->phi_KV = c->kbuf = c->alpha_ss = c->e_dead = c->wsum = nullptr;
+    c->Bt32 = nullptr;
     c->model_set = false;
 }
 
@@ -666,6 +674,37 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
     timer.end(ctx->stream);
     CK(cudaGetLastError());
     st->n_launches++;
+    return 0;
+}
+
+// Precision sweep (BASELINE.json configs[3]): PYLDA_PRECISION = f64s | tile32 | f32 runs estep_sweep.cuh instead of
+// the product kernels (measurement tool; K <= 256).
+int launch_estep_sweep(pylda_ctx* ctx, Corpus& cp, const char* mode, int max_iter, double tol, pylda_stats* st) {
+    const int K = ctx->K, KP = ctx->KP;
+    if (K > 256) return fail(ctx, "PYLDA_PRECISION=%s: the sweep kernel handles K <= 256 (got %d)", mode, K);
+    EParams p;
+    memset(&p, 0, sizeof p);
+    p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+    p.order = cp.order; p.ndocs = (int)cp.D;
+    p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha;
+    p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
+    p.K = K; p.KP = KP; p.max_iter = max_iter; p.tol = tol;
+    const int grid = ctx->prop.multiProcessorCount * 8;
+    if (!strcmp(mode, "f64s")) {
+        estep_sweep<double, double><<<grid, 256, 0, ctx->stream>>>(p, ctx->Bt);
+    } else {
+        const size_t n = (size_t)ctx->V * KP;
+        if (!ctx->Bt32) CK(cudaMalloc((void**)&ctx->Bt32, n * sizeof(float)));
+        k_convert_table<float><<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->Bt, n, ctx->Bt32);
+        if (!strcmp(mode, "tile32")) estep_sweep<float, double><<<grid, 256, 0, ctx->stream>>>(p, ctx->Bt32);
+        else if (!strcmp(mode, "f32")) estep_sweep<float, float><<<grid, 256, 0, ctx->stream>>>(p, ctx->Bt32);
+        else return fail(ctx, "PYLDA_PRECISION must be f64s, tile32 or f32 (got %s)", mode);
+        st->n_launches++;
+    }
+    CK(cudaGetLastError());
+    st->n_launches++;
+    st->n_estep_launches++;
+    st->docs_streamed = cp.D;
     return 0;
 }
 
@@ -1175,8 +1214,10 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     {
         const char* kv = getenv("PYLDA_KERNEL");
-        const int rc = (kv && !strcmp(kv, "v1")) ? launch_estep_v1(ctx, cp, max_iter, tol, &st)
-                                                 : launch_estep(ctx, cp, max_iter, tol, &st);
+        const char* pv = getenv("PYLDA_PRECISION");
+        const int rc = (pv && *pv && strcmp(pv, "f64")) ? launch_estep_sweep(ctx, cp, pv, max_iter, tol, &st)
+                       : (kv && !strcmp(kv, "v1"))      ? launch_estep_v1(ctx, cp, max_iter, tol, &st)
+                                                        : launch_estep(ctx, cp, max_iter, tol, &st);
         if (rc) return 1;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1348,6 +1389,29 @@ int pylda_get_eta(pylda_ctx* ctx, double* eta_KxV) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(eta_KxV, ctx->eta, (size_t)ctx->K * ctx->V * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pylda_top_words(pylda_ctx* ctx, int top, int32_t* idx_KxT, double* prob_KxT) {
+    if (!ctx) return 1;
+    if (!ctx->model_set) return fail(ctx, "pylda_top_words: no model on the device (pylda_set_model)");
+    if (top < 1 || top > ctx->V || !idx_KxT || !prob_KxT) return fail(ctx, "pylda_top_words: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int K = ctx->K, V = ctx->V, KP = ctx->KP;
+    // E_log_eta of the CURRENT eta and its per-topic logsumexp (the statistics accumulator is left alone)
+    k_rowsum_psi<<<K, 256, 0, ctx->stream>>>(ctx->eta, K, V, ctx->kbuf, ctx->kbuf + K);
+    dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
+    k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(ctx->eta, ctx->kbuf, K, V, KP, ctx->Elt);
+    const int nchunk = 64;
+    if (ensure_partial(ctx, (size_t)2 * nchunk * K)) return 1;
+    dim3 lg((K + 31) / 32, nchunk);
+    k_lse_partial<<<lg, 256, 0, ctx->stream>>>(ctx->Elt, K, V, KP, ctx->partial, ctx->partial + (size_t)nchunk * K);
+    k_lse_final<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial, ctx->partial + (size_t)nchunk * K, K, nchunk,
+                                                         ctx->kbuf + 2 * K);
+    CK(cudaGetLastError());
+    std::string err;
+    if (device_top_words(ctx->Elt, ctx->kbuf + 2 * K, K, V, KP, top, idx_KxT, prob_KxT, ctx->stream, &err))
+        return fail(ctx, "pylda_top_words: %s", err.c_str());
     return 0;
 }
 

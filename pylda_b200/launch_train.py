@@ -25,6 +25,9 @@ FLAGS = (  # name, type, default, help   (launch_train.py:12-62)
     ("alpha_alpha", "float", -1, "hyper-parameter for Dirichlet distribution of topics [1.0/number_of_topics]"),
     ("alpha_beta", "float", -1, "hyper-parameter for Dirichlet distribution of vocabulary [1.0/number_of_types]"),
     ("inference_mode", "int", 0, "inference mode [0 (default): hybrid, 1: monte carlo, 2: variational bayes]"),
+    # not in the reference: directory of the on-disk CSR cache of the parsed corpus (pylda_b200/corpus_cache.py);
+    # in a multi-process run rank 0 parses once and every rank reads only its own shard of documents
+    ("csr_cache", "string", None, "directory of the on-disk CSR cache of the parsed corpus [None: parse in every process]"),
 )
 
 
@@ -56,6 +59,8 @@ def main(argv=None):
     assert options.input_directory is not None
     assert options.output_directory is not None
     number_of_topics = options.number_of_topics
+    if options.csr_cache:
+        os.environ["PYLDA_CSR_CACHE"] = options.csr_cache
     training_iterations = options.training_iterations
     snapshot_interval = options.snapshot_interval
     inference_mode = options.inference_mode

@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -66,6 +66,7 @@ _SIGNATURES = {
     "pylda_set_alpha": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "pylda_dirichlet_expectation": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                                    _c_double_p, _c_double_p]),
+    "pylda_top_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int32_p, _c_double_p]),
     "pylda_special": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, _c_double_p, _c_double_p]),
     "pylda_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "pylda_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
@@ -243,6 +244,14 @@ class EStepContext(object):
         eta = numpy.empty((self.K, self.V), dtype=numpy.float64)
         self._check(self._lib.pylda_get_eta(self._h, _dp(eta)), "pylda_get_eta")
         return eta
+
+    def top_words(self, top):
+        """(idx (K, top) int32, prob (K, top) float64): the `top` most probable words of every topic of the model on
+        the device, most probable first (device side of export_beta, variational_bayes.py:326-341)."""
+        idx = numpy.empty((self.K, top), dtype=numpy.int32)
+        prob = numpy.empty((self.K, top), dtype=numpy.float64)
+        self._check(self._lib.pylda_top_words(self._h, int(top), idx.ctypes.data_as(_c_int32_p), _dp(prob)), "pylda_top_words")
+        return idx, prob
 
     # -- helpers exposed for parity tests -----------------------------------------------------
     def dirichlet_expectation(self, eta):

@@ -15,7 +15,7 @@ import numpy
 import scipy.special
 
 from .inferencer import Inferencer, compute_dirichlet_expectation
-from . import distributed, native
+from . import corpus_cache, distributed, native
 
 
 def pack_parsed_corpus(parsed_corpus):
@@ -86,6 +86,9 @@ class VariationalBayes(Inferencer):
         state["_alpha_ss_device"] = None
         state["_model_on_device"] = False
         state.pop("_last_parsed_csr", None)                    # (attribute of older versions)
+        state.pop("_train_shard", None)
+        if isinstance(state.get("_parsed_corpus"), corpus_cache.LazyParsed):
+            state["_parsed_corpus"] = tuple(state["_parsed_corpus"]._materialize())
         return state
 
     def _context(self):
@@ -110,9 +113,12 @@ class VariationalBayes(Inferencer):
 
     def _upload_train(self, ctx):
         if not self._train_uploaded:
-            if getattr(self, "_train_csr", None) is None:
-                self._train_csr = pack_parsed_corpus(self._parsed_corpus)
-            lo, hi, shard = self._shard(self._train_csr)
+            if getattr(self, "_train_shard", None) is not None:
+                lo, hi, shard = self._train_shard              # read from the on-disk CSR cache: this rank's rows only
+            else:
+                if getattr(self, "_train_csr", None) is None:
+                    self._train_csr = pack_parsed_corpus(self._parsed_corpus)
+                lo, hi, shard = self._shard(self._train_csr)
             ctx.set_corpus(0, *shard)
             self._gamma_rows = (lo, hi)
             self._train_uploaded = True
@@ -130,8 +136,16 @@ class VariationalBayes(Inferencer):
     def _initialize(self, corpus, vocab, number_of_topics, alpha_alpha, alpha_beta):
         # :82-95
         Inferencer._initialize(self, vocab, number_of_topics, alpha_alpha, alpha_beta)
-        self._parsed_corpus, csr = self._parse(corpus)
-        self._number_of_documents = len(self._parsed_corpus[0])
+        self.__dict__.pop("_train_shard", None)
+        cache_dir = os.environ.get("PYLDA_CSR_CACHE")
+        if cache_dir:
+            # on-disk CSR (corpus_cache.py): rank 0 parses once, every rank maps the files and reads its shard only
+            csr = None
+            self._parsed_corpus = self._parse_cached(corpus, cache_dir)
+            self._number_of_documents = self._parsed_corpus.number_of_documents
+        else:
+            self._parsed_corpus, csr = self._parse(corpus)
+            self._number_of_documents = len(self._parsed_corpus[0])
         self._gamma = numpy.zeros((self._number_of_documents, self._number_of_topics)) \
             + self._alpha_alpha[numpy.newaxis, :] + 1.0 * self._number_of_types / self._number_of_topics
         # the only random draw that affects VB results (:95); same global-RNG call as the reference
@@ -139,7 +153,10 @@ class VariationalBayes(Inferencer):
         # (the native parser already produced the CSR of exactly this corpus; checked, never trusted blindly)
         if csr is not None and len(csr[0]) - 1 != self._number_of_documents:
             csr = None
-        self._train_csr = csr if csr is not None else pack_parsed_corpus(self._parsed_corpus)
+        if cache_dir:
+            self._train_csr = None
+        else:
+            self._train_csr = csr if csr is not None else pack_parsed_corpus(self._parsed_corpus)
         self._train_uploaded = False
         rank, size, _ = distributed.world()
         if size > 1:
@@ -147,6 +164,26 @@ class VariationalBayes(Inferencer):
             if rank != 0:
                 self._eta[:] = 0.0
             self._context().allreduce_sum(self._eta)
+
+    def _parse_cached(self, corpus, cache_dir):
+        """The training corpus through the on-disk CSR cache: parsed by rank 0 only when the entry is missing; this
+        rank keeps its own shard (self._train_shard) and a lazy stand-in for the (word_ids, word_cts) lists."""
+        rank, size, _ = distributed.world()
+        key, vocab_sha1, corpus_sha1 = corpus_cache.cache_key(corpus, self._index_to_type)
+        entry = corpus_cache.open_entry(cache_dir, key)
+        if entry is None:
+            if rank == 0:
+                parsed, csr = self._parse(corpus)
+                dropped = len(corpus) - len(parsed[0])
+                corpus_cache.save(cache_dir, key, csr if csr is not None else pack_parsed_corpus(parsed), dropped,
+                                  vocab_sha1, corpus_sha1)
+            else:
+                corpus_cache.wait_for(cache_dir, key)
+            entry = corpus_cache.open_entry(cache_dir, key)
+        else:
+            print("successfully parse %d documents..." % entry[0]["D"])
+        self._train_shard = corpus_cache.load_shard(entry, rank, size)
+        return corpus_cache.LazyParsed(entry)
 
     def parse_data(self, corpus):
         # :98-130 -- per document: unique in-vocabulary type ids (first-seen order) and counts;
@@ -216,7 +253,7 @@ class VariationalBayes(Inferencer):
         else:
             self._upload_train(ctx)
             lo, hi = self._gamma_rows
-            slot, number_of_documents = 0, len(self._parsed_corpus[0])
+            slot, number_of_documents = 0, self._number_of_documents
         # the reference visits documents in numpy.random.permutation order (:159); the order only
         # changes fp summation order, but the draw keeps the global RNG stream in step with it
         numpy.random.permutation(number_of_documents)
@@ -278,7 +315,7 @@ class VariationalBayes(Inferencer):
         self._upload_train(ctx)
         if not self.__dict__.get("_model_on_device"):
             ctx.set_model(self._eta, self._alpha_alpha)
-        numpy.random.permutation(len(self._parsed_corpus[0]))          # RNG stream of :159
+        numpy.random.permutation(self._number_of_documents)            # RNG stream of :159
         self._last_estep_stats = ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
         res = ctx.get_results(0, gamma=False, phi=False, alpha_ss=True)
         clock_e_step = time.time() - clock_e_step
@@ -366,6 +403,20 @@ class VariationalBayes(Inferencer):
 
     def export_beta(self, exp_beta_path, top_display=-1):
         # :326-341
+        if self.__dict__.get("_native") is not None and os.environ.get("PYLDA_DEVICE_EXPORT", "1") != "0":
+            # device path: per-topic sort on the device, only the displayed words come back
+            ctx = self._native
+            if not self.__dict__.get("_model_on_device"):
+                ctx.set_model(self._eta, self._alpha_alpha)
+                self.__dict__["_model_on_device"] = True
+            top = self._number_of_types if top_display <= 0 else min(top_display, self._number_of_types)
+            idx, prob = ctx.top_words(top)
+            with open(exp_beta_path, 'w') as output:
+                for topic_index in range(self._number_of_topics):
+                    output.write("==========\t%d\t==========\n" % topic_index)
+                    for type_index, p in zip(idx[topic_index], prob[topic_index]):
+                        output.write("%s\t%g\n" % (self._index_to_type[int(type_index)], p))
+            return
         E_log_eta = compute_dirichlet_expectation(self._eta)
         with open(exp_beta_path, 'w') as output:
             for topic_index in range(self._number_of_topics):

@@ -77,3 +77,26 @@ def test_config5_shape_reduced_docs(ctx):
     lane shape; the full V=1M table is 4 GB per copy and is exercised by the bench, not by a test)."""
     out = _properties_and_subsample(ctx, 20000, 100000, 500, "poisson", 1238, 24)
     print("config5-shape stats", out["stats"])
+
+
+def test_config4_full_nips_corpus_fp64(ctx):
+    """BASELINE.json configs[3] in full: nips.88-05 (2 483 documents, V = 3 209), K = 200, EM iteration 1, against
+    the unmodified reference's output (tests/golden/nips_full_k200.npz: gamma in full, every 16th occurring phi_ss
+    column, the phi_ss row and column sums, the ELBO, per-document trip counts)."""
+    import os
+    from pylda_b200 import synthetic
+    from tests.util import GOLDEN, RTOL, PHI_FLOOR, max_rel
+    g = numpy.load(os.path.join(GOLDEN, "nips_full_k200.npz"))
+    K, V = int(g["K"]), int(g["V"])
+    row_ptr, ids, cts = g["row_ptr"].astype(numpy.int64), g["ids"].astype(numpy.int32), g["cts"].astype(numpy.int32)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, synthetic.initial_eta(K, V, int(g["eta_seed"])), g["alpha"], 50, 1e-6)
+    it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    assert out["stats"]["revived_docs"] == 0
+    assert max_rel(out["gamma"], g["gamma"]) <= RTOL
+    assert max_rel(out["phi_ss"][:, g["phi_cols"]], g["phi_ss_cols"], floor=PHI_FLOOR) <= RTOL
+    assert max_rel(out["phi_ss"].sum(axis=1), g["phi_rowsum"]) <= RTOL
+    assert max_rel(out["phi_ss"].sum(axis=0), g["phi_colsum"], floor=PHI_FLOOR) <= RTOL
+    assert abs(out["doc_ll"] - float(g["doc_ll"])) <= RTOL * abs(float(g["doc_ll"]))
+    assert numpy.mean(it == g["iters"]) >= 0.999
+    print("config 4 full: kernel %.2f ms, mean trips %.1f, stats %s" % (out["stats"]["kernel_ms"], it.mean(), out["stats"]))

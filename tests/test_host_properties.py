@@ -45,3 +45,44 @@ def test_shards_partition_the_corpus(docs, n_ranks):
         longest = int(numpy.diff(row_ptr).max())
         nnz = numpy.array([len(p[1]) for p in parts])
         assert nnz.max() - nnz.min() <= 2 * longest + 1 or n_ranks > len(docs)
+
+
+def test_csr_cache_round_trip_and_shards(tmp_path):
+    """On-disk CSR cache: what rank 0 writes is bit-identical to the parsed corpus, every rank's
+    shard is exactly its nnz-balanced slice, a different vocabulary order gives a different key, and the lazy
+    stand-in for (word_ids, word_cts) materialises the reference's list type."""
+    import numpy
+    from pylda_b200 import corpus_cache, native
+    from pylda_b200 import variational_bayes as vb
+    V = 300
+    rs = numpy.random.RandomState(3)
+    docs = [" ".join("w%d" % t for t in rs.randint(0, V + 20, rs.randint(1, 60))) for _ in range(400)] + ["zzz"]
+    vocab = ["w%d" % i for i in range(V)]
+    a = vb.VariationalBayes(); a.parse_vocabulary(vocab)
+    parsed, csr = a._parse(docs)
+    csr = csr if csr is not None else vb.pack_parsed_corpus(parsed)
+    key, vs, cs = corpus_cache.cache_key(docs, a._index_to_type)
+    assert corpus_cache.open_entry(str(tmp_path), key) is None
+    corpus_cache.save(str(tmp_path), key, csr, len(docs) - len(parsed[0]), vs, cs)
+    entry = corpus_cache.open_entry(str(tmp_path), key)
+    meta, row_ptr, ids, cts = entry
+    D = len(parsed[0])
+    assert meta["D"] == D and 390 <= D <= 400 and meta["dropped"] == len(docs) - D >= 1
+    assert numpy.array_equal(row_ptr, csr[0]) and numpy.array_equal(ids, csr[1]) and numpy.array_equal(cts, csr[2])
+    bounds = native.shard_bounds(csr[0], 3)
+    seen = 0
+    for r in range(3):
+        lo, hi, (rp, i2, c2) = corpus_cache.load_shard(entry, r, 3)
+        assert (lo, hi) == (int(bounds[r]), int(bounds[r + 1])) and rp[0] == 0
+        a0, a1 = int(csr[0][lo]), int(csr[0][hi])
+        assert numpy.array_equal(rp, csr[0][lo:hi + 1] - a0) and numpy.array_equal(i2, csr[1][a0:a1]) and numpy.array_equal(c2, csr[2][a0:a1])
+        seen += hi - lo
+    assert seen == D
+    lazy = corpus_cache.LazyParsed(entry)
+    assert lazy.number_of_documents == D and len(lazy) == 2
+    for x, y in zip(lazy[0], parsed[0]):
+        assert numpy.array_equal(x, y)
+    for x, y in zip(lazy[1], parsed[1]):
+        assert x.shape == y.shape and numpy.array_equal(x, y)
+    b = vb.VariationalBayes(); b.parse_vocabulary(list(reversed(vocab)))
+    assert corpus_cache.cache_key(docs, b._index_to_type)[0] != key

@@ -83,7 +83,8 @@ def _train_rank(rank, world, tmp, port):
     from pylda_b200 import launch_train
     numpy.random.seed(100 + rank)        # different draws on purpose: rank 0's eta0 must win
     launch_train.main(["--input_directory=%s" % os.path.join(tmp, "toy"), "--output_directory=%s" % os.path.join(tmp, "out"),
-                       "--number_of_topics=6", "--training_iterations=3", "--snapshot_interval=3", "--inference_mode=2"])
+                       "--number_of_topics=6", "--training_iterations=3", "--snapshot_interval=3", "--inference_mode=2",
+                       "--csr_cache=%s" % os.path.join(tmp, "cache")])      # rank 0 parses, both ranks read their shard
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs at least 2 GPUs")
@@ -113,5 +114,16 @@ def test_launch_train_two_processes_matches_one(capfd):
         assert len(run) == 1
         files = sorted(os.listdir(os.path.join(tmp, "out", "toy", run[0])))
         assert files == ["exp_beta-3", "exp_gamma-3", "model-3", "option.txt"]
+        # exp_gamma holds ALL documents (variational_bayes.py:343-356), gathered from both ranks' shards, and the
+        # pickled model carries the full gamma as well
+        run1 = os.listdir(os.path.join(tmp, "single", "toy"))[0]
+        g2 = open(os.path.join(tmp, "out", "toy", run[0], "exp_gamma-3")).read().split("\n")
+        g1 = open(os.path.join(tmp, "single", "toy", run1, "exp_gamma-3")).read().split("\n")
+        assert len(g2) == len(g1) == 91 and sum(a == b for a, b in zip(g1, g2)) >= 88
+        import pickle
+        with open(os.path.join(tmp, "out", "toy", run[0], "model-3"), "rb") as f:
+            model = pickle.load(f)
+        assert model._gamma.shape == (90, 6) and isinstance(model._parsed_corpus, tuple) and len(model._parsed_corpus[0]) == 90
+        assert os.path.exists(os.path.join(tmp, "cache"))
     assert len(single) == 3 and len(multi) == 6                      # both ranks print every iteration
     assert sorted(set(multi)) == sorted(set(single))                 # the same 6-digit ELBO values

@@ -135,3 +135,25 @@ def test_launch_train_and_test_drivers(tmp_path, capsys):
     assert numpy.isfinite(ll) and ll < 0 and gam.shape == (10, K)
     saved = numpy.loadtxt(os.path.join(run_dir, "test-4"))
     assert numpy.allclose(saved, gam, rtol=1e-12)
+
+
+def test_device_top_words_match_host_export(ctx, tmp_path):
+    """pylda_top_words (device side of export_beta, variational_bayes.py:326-341) against the reference's host
+    formula: per topic exp(E_log_eta - logsumexp) sorted descending; and the exported file is the same text."""
+    import os
+    import scipy.special
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V = 30, 900
+    rs = numpy.random.RandomState(5)
+    eta = rs.gamma(0.3, 1.0, (K, V)) + 1e-3
+    ctx.set_model(eta, numpy.full(K, 0.1))
+    idx, prob = ctx.top_words(25)
+    E = O.compute_dirichlet_expectation(eta)
+    beta = numpy.exp(E - scipy.special.logsumexp(E, axis=1)[:, None])
+    order = numpy.argsort(-beta, axis=1)[:, :25]
+    assert numpy.allclose(prob, numpy.take_along_axis(beta, order, axis=1), rtol=1e-12)
+    assert numpy.array_equal(idx, order)          # (continuous random eta: no ties)
+    full_idx, full_prob = ctx.top_words(V)
+    assert numpy.array_equal(numpy.sort(full_idx, axis=1), numpy.tile(numpy.arange(V), (K, 1)))
+    assert numpy.all(numpy.diff(full_prob, axis=1) <= 0) and numpy.allclose(full_prob.sum(axis=1), 1.0, rtol=1e-12)
