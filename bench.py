@@ -427,6 +427,7 @@ def run_product(args, cfg):
         res = ctx.get_results(0, gamma=False, phi=False)
         results[state] = dict(dev_ms=allmax(sum(dev) / len(dev)), wall_ms=allmax(1e3 * wall / args.steps),
                               ker_ms=allmax(sum(ker) / len(ker)), stats=st, doc_ll=res["doc_ll"],
+                              allreduce_ms=allmax(st["allreduce_ms"]),
                               mean_trips=st["inner_iters"] / docs_total, at_cap=st["docs_at_cap"])
         if state == args.state:
             # ---- self-check of the timed state (every N): the two invariants of the E-step ----
@@ -530,7 +531,8 @@ def run_product(args, cfg):
                         (12.0 * nnz + 8.0 * D * (K + 2) + 4 * 8.0 * V * K) / 1e9),
                     "parallelism": "dp%d, one process per GPU, one NCCL all-reduce of K x V f64 per step" % world,
                     "timing": "CUDA events on the library's stream, per step, max over ranks",
-                    "docs_narrow_stages": [int(st["docs_narrow_wide"]), int(st["docs_narrow"])]},
+                    "docs_narrow_stages": [int(st["docs_narrow_wide"]), int(st["docs_narrow"])],
+                    "allreduce_ms": head["allreduce_ms"]},
             "wall_ms_per_step": head["wall_ms"],
             "elbo_doc_ll": head["doc_ll"],
             "check": check,

@@ -57,8 +57,11 @@ typedef struct pylda_stats {
     int64_t revived_docs;      /* documents in which a topic eliminated as dead (gamma_k == alpha_k) would have
                                   come back (summed over ranks).  0 in every corpus seen so far; when it is not, the
                                   library has already redone the E-step at full width and the results are those */
-    int64_t docs_narrow_wide;     /* documents handed to the 16-column narrow stage (at most 16 topics alive)     */
-    int64_t docs_narrow;      /* documents that went through the 8-column narrow stage (at most 8 alive)      */
+    int64_t docs_narrow_wide;  /* documents handed to the 32- / 16-column narrow stages (at most 32 / 16 topics alive;
+                                  a document that passes both is counted twice)                                  */
+    int64_t docs_narrow;       /* documents that went through the 8-column narrow stage (at most 8 alive)      */
+    double  allreduce_ms;      /* NCCL all-reduce of the V x K statistics, ELBO scalars and alpha statistics
+                                  (CUDA-event time on our stream; part of post_ms; 0 on a single rank)          */
 } pylda_stats;
 
 /* ABI version of the loaded library (== PYLDA_ABI_VERSION of the header it was built from). */

@@ -107,7 +107,7 @@ struct pylda_ctx {
     int device = 0;
     cudaDeviceProp prop;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     Corpus corp[2];
     // model
@@ -1236,12 +1236,20 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
         ctx->have_alpha_ss = true;
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (ctx->comm) {
         // [scal5] = local D so that doc_ll can add D_total * alpha_term
         const double dloc = (double)cp.D;
         CK(cudaMemcpyAsync(ctx->scal + 7, &dloc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        // One all-reduce per E-step.  The V x K statistics go in V-range chunks of at most 1 GB inside
+        // one NCCL group (4 GB at V = 1M, K = 500): NCCL pipelines them over NVLink; there is nothing to overlap
+        // them with -- any document can touch any word, so the statistics are complete only when the last
+        // per-document kernel has finished, and the ELBO reduction above must read the LOCAL statistics first.
         int rc = g_nccl.GroupStart();
-        if (!rc) rc = g_nccl.AllReduce(ctx->phi, ctx->phi, (size_t)V * KP, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+        const size_t total = (size_t)V * KP, chunk = (size_t)1 << 27;
+        for (size_t o = 0; o < total && !rc; o += chunk)
+            rc = g_nccl.AllReduce(ctx->phi + o, ctx->phi + o, std::min(chunk, total - o), kNcclFloat64, kNcclSum, ctx->comm,
+                                  ctx->stream);
         if (!rc) rc = g_nccl.AllReduce(ctx->scal, ctx->scal, 8, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
         if (!rc && want_alpha_ss)
             rc = g_nccl.AllReduce(ctx->alpha_ss, ctx->alpha_ss, (size_t)K, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
@@ -1249,6 +1257,7 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
         if (rc || rc2) return fail(ctx, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc ? rc : rc2));
     }
     ctx->phi_KV_valid = false;
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaMemcpyAsync(ctx->last_scal, ctx->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1260,6 +1269,7 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st.kernel_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st.post_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); st.total_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); st.allreduce_ms = ctx->comm ? ms : 0.0;
     st.n_docs = cp.D;
     st.nnz = cp.nnz;
     st.inner_iters = (int64_t)llround(ctx->last_scal[3]);

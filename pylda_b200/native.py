@@ -37,6 +37,7 @@ class Stats(ctypes.Structure):
         ("revived_docs", ctypes.c_int64),
         ("docs_narrow_wide", ctypes.c_int64),
         ("docs_narrow", ctypes.c_int64),
+        ("allreduce_ms", ctypes.c_double),
     ]
 
     def as_dict(self):
