@@ -214,18 +214,6 @@ bool pick_shape(int K, int* LK, int* J, bool v2 = false, int W = 8) {
     return found;
 }
 
-const void* lookup_kernel(int LK, int J, bool res) {
-    switch (LK) {
-        case 1: return estep_kernel_lk1(J, res);
-        case 2: return estep_kernel_lk2(J, res);
-        case 4: return estep_kernel_lk4(J, res);
-        case 8: return estep_kernel_lk8(J, res);
-        case 16: return estep_kernel_lk16(J, res);
-        case 32: return estep_kernel_lk32(J, res);
-    }
-    return nullptr;
-}
-
 const void* lookup_v2(int LK, int J, int W, int V) {
     switch (LK) {
         case 1: return estep_v2_lk1(J, W, V);
@@ -263,22 +251,6 @@ struct GroupLayout {
     int off_gam, off_spart, off_red, off_cnt, off_mwr, off_rid, off_tile, bytes;
 };
 int align_up(int x, int a) { return (x + a - 1) / a * a; }
-GroupLayout group_layout(int W, int KPAD, int nmax, int ST, bool res) {
-    GroupLayout g;
-    int o = 16;                       // mbarrier + queue slot
-    o += KPAD * 8;                    // es
-    g.off_gam = o;   o += KPAD * 8;
-    g.off_spart = o; o += W * KPAD * 8;
-    g.off_red = o;   o += 16 * 8;
-    g.off_cnt = o;   if (res) o += nmax * 8;
-    g.off_mwr = o;   if (res) o += nmax * 8;
-    g.off_rid = o;   if (res) o += nmax * 4;
-    o = align_up(o, 16);
-    g.off_tile = o;  if (res) o += nmax * ST * 8;
-    g.bytes = align_up(o, 128);
-    return g;
-}
-
 // shared-memory layout of one document group of estep_v2 (W warps)
 GroupLayout group_layout_v2(int W, int LK, int KPAD, int nmax, int ST) {
     GroupLayout g;
@@ -310,24 +282,6 @@ GroupLayout group_layout_rt(int W, int LK, int KPAD, int cap, int ST) {
     g.off_gam = 0;
     g.off_spart = o; o += NP * KPAD * 8;
     g.off_red = o;   o += align_up(4 * W + 2, 2) * 8;   // dsum [W], ELBO pairs [2W], live counts [W]
-    g.off_cnt = o;   o += cap * 8;
-    g.off_mwr = o;   o += cap * 8;
-    g.off_rid = o;   o += cap * 4;
-    o = align_up(o, 16);
-    g.off_tile = o;  o += cap * ST * 8 + KPAD * 8;
-    g.bytes = align_up(o, 128);
-    return g;
-}
-
-// shared-memory layout of one CTA of estep_cl (8 warps, `cap` rows of the document slice)
-GroupLayout group_layout_cl(int KPAD, int cap, int ST) {
-    GroupLayout g;
-    const int W = 8;
-    int o = 16;
-    o += KPAD * 8;                    // es
-    g.off_spart = o; o += W * KPAD * 8;
-    g.off_red = o;   o += align_up(4 * W + 2, 2) * 8;   // dsum [W], ELBO pairs [2W], live counts [W]
-    g.off_gam = o;   o += 2 * 8 * KPAD * 8;   // exchange slots [2][8][KPAD]
     g.off_cnt = o;   o += cap * 8;
     g.off_mwr = o;   o += cap * 8;
     g.off_rid = o;   o += cap * 4;
@@ -386,83 +340,10 @@ int prepare_tables(pylda_ctx* ctx, bool heldout, int* launches) {
     return 0;
 }
 
-int launch_estep_v1(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
-    const int K = ctx->K, KP = ctx->KP;
-    int LK = 0, J = 0;
-    if (!pick_shape(K, &LK, &J)) return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
-    const int KPAD = 2 * LK * J;
-    const int ST = tile_stride(KP, LK);
-    const int smem_budget = (int)ctx->prop.sharedMemPerBlockOptin;
-    const int cta_fixed = align_up(KPAD * 8, 128);
-    const int Ws[4] = {1, 2, 4, 8};
-    int cap[4];
-    for (int i = 0; i < 4; ++i) {
-        const int W = Ws[i], G = 8 / W;
-        const int avail = ((smem_budget - cta_fixed) / G) & ~127;
-        const GroupLayout g0 = group_layout(W, KPAD, 0, ST, true);
-        int n = (avail - g0.bytes - 128) / (ST * 8 + 20);
-        n &= ~3;
-        cap[i] = std::max(n, 0);
-    }
-    // class boundaries in the length-sorted (descending) order
-    const std::vector<int>& ns = cp.n_sorted;
-    const long long D = cp.D;
-    auto first_leq = [&](int limit) -> long long {   // first index whose n <= limit
-        return std::partition_point(ns.begin(), ns.end(), [&](int n) { return n > limit; }) - ns.begin();
-    };
-    long long b8 = first_leq(cap[3]);   // [0,b8): streaming
-    long long b4 = first_leq(cap[2]);   // [b8,b4): W=8
-    long long b2 = first_leq(cap[1]);   // [b4,b2): W=4
-    long long b1 = first_leq(cap[0]);   // [b2,b1): W=2 ; [b1,D): W=1
-    b4 = std::max(b4, b8); b2 = std::max(b2, b4); b1 = std::max(b1, b2);
-    struct Cls { long long lo, hi; int W; bool res; };
-    const Cls classes[5] = {{0, b8, 8, false}, {b8, b4, 8, true}, {b4, b2, 4, true}, {b2, b1, 2, true}, {b1, D, 1, true}};
-    CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(int), ctx->stream));
-    st->docs_streamed = b8;
-    st->docs_resident = D - b8;
-    for (int ci = 0; ci < 5; ++ci) {
-        const Cls& c = classes[ci];
-        const long long nd = c.hi - c.lo;
-        if (nd <= 0) continue;
-        const void* fn = lookup_kernel(LK, J, c.res);
-        if (!fn) return fail(ctx, "no kernel instantiation for LK=%d J=%d", LK, J);
-        const int G = 8 / c.W;
-        int nmax = 0;
-        if (c.res) nmax = std::max(4, (ns[c.lo] + 3) & ~3);
-        const GroupLayout gl = group_layout(c.W, KPAD, nmax, ST, c.res);
-        const int smem = cta_fixed + G * gl.bytes;
-        if (smem > smem_budget) return fail(ctx, "internal: class %d needs %d B of shared memory", ci, smem);
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, smem, 0));
-        if (occ < 1) return fail(ctx, "internal: zero occupancy for class %d (smem %d)", ci, smem);
-        long long grid = (long long)ctx->prop.multiProcessorCount * occ;
-        grid = std::min(grid, (nd + G - 1) / G);
-        EParams p;
-        p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
-        p.order = cp.order + c.lo; p.ndocs = (int)nd; p.counter = ctx->counters + ci;
-        p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
-        p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
-        p.W = c.W; p.nmax = nmax; p.group_bytes = gl.bytes; p.off_groups = cta_fixed;
-        p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
-        p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
-        void* args[] = {&p};
-        CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)smem, ctx->stream));
-        st->n_launches++;
-        st->n_estep_launches++;
-    }
-    return 0;
-}
-
 // Length classes of the single-CTA resident paths.  Documents are sorted by n_d (descending); every
 // class has a row capacity and a document goes to the class with the smallest capacity that holds it.
-//   "WxG"  estep_v2: tile in shared memory, W warps per document, G documents in flight per CTA
-//          (W*G <= 8: 8-warp CTAs; 8 < W*G <= 16: the 16-warp variant);
-//   "rW"   estep_rt: tile in registers, W warps per document, 8/W documents in flight per CTA;
-//   "rW/RxG[@LK:J]"  an explicitly compiled estep_rt variant with R rows per lane and G documents per CTA
-//          (12- and 16-warp CTAs; measured slower than the defaults -- multi-warp groups pay barriers and
-//          duplicated owner phases -- kept as a tuning aid).
+//   "8x1"  estep_v2: tile in shared memory, 8 warps per document, one document per CTA;
+//   "rW"   estep_rt: tile in registers, W warps per document, 8/W documents in flight per CTA.
 // PYLDA_CLASSES overrides the default list (tuning aid).
 struct ClassCfg { int kind, W, G, R, LK, J; };
 
@@ -476,16 +357,11 @@ std::vector<ClassCfg> class_config(bool use_hy) {
         size_t end = spec.find(',', pos);
         if (end == std::string::npos) end = spec.size();
         const std::string item = spec.substr(pos, end - pos);
-        int W = 0, G = 0, R = 0, LK = 0, J = 0;
-        const int nf = sscanf(item.c_str(), "r%d/%dx%d@%d:%d", &W, &R, &G, &LK, &J);
-        if (nf >= 3) {                    // explicit register-tile variant "rW/RxG[@LK:J]" (must be compiled)
-            if (nf != 5) LK = J = 0;
-            if ((W == 1 || W == 2 || W == 4 || W == 8) && R >= 1 && G >= 1 && W * G <= 16) out.push_back({1, W, G, R, LK, J});
-        } else if (sscanf(item.c_str(), "r%d", &W) == 1) {
+        int W = 0;
+        if (sscanf(item.c_str(), "r%d", &W) == 1) {
             if (W == 1 || W == 2 || W == 4 || W == 8) out.push_back({1, W, 8 / W, 0, 0, 0});
-        } else if (sscanf(item.c_str(), "%dx%d", &W, &G) == 2 &&
-                   (W == 1 || W == 2 || W == 4 || W == 8) && G >= 1 && W * G <= (W > 1 ? 16 : 8)) {
-            out.push_back({0, W, G, 0, 0, 0});
+        } else if (item == "8x1") {
+            out.push_back({0, 8, 1, 0, 0, 0});
         }
         pos = end + 1;
     }
@@ -519,38 +395,6 @@ struct ClassTimer {
     }
 };
 
-int launch_streaming(pylda_ctx* ctx, Corpus& cp, long long nd, int LK, int J, int max_iter, double tol, pylda_stats* st,
-                     int counter_slot) {
-    const int K = ctx->K, KP = ctx->KP;
-    const int KPAD = 2 * LK * J;
-    const int ST = tile_stride(KP, LK);
-    const void* fn = lookup_kernel(LK, J, false);
-    if (!fn) return fail(ctx, "no kernel instantiation for LK=%d J=%d", LK, J);
-    const int cta_fixed = align_up(KPAD * 8, 128);
-    const GroupLayout gl = group_layout(8, KPAD, 0, ST, false);
-    const int smem = cta_fixed + gl.bytes;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, smem, 0));
-    if (occ < 1) return fail(ctx, "internal: zero occupancy for the streaming class (smem %d)", smem);
-    long long grid = std::min<long long>((long long)ctx->prop.multiProcessorCount * occ, nd);
-    EParams p;
-    memset(&p, 0, sizeof p);
-    p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
-    p.order = cp.order; p.ndocs = (int)nd; p.counter = ctx->counters + counter_slot;
-    p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-    p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
-    p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
-    p.W = 8; p.nmax = 0; p.group_bytes = gl.bytes; p.off_groups = cta_fixed;
-    p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
-    p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
-    void* args[] = {&p};
-    CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)smem, ctx->stream));
-    st->n_launches++;
-    st->n_estep_launches++;
-    return 0;
-}
-
 // second-generation streaming kernel for documents [lo, hi) of the sorted order (all with n <= nmax)
 int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int nmax, int LK, int J, int max_iter,
                    double tol, pylda_stats* st, int counter_slot, int* launched, int park_nc) {
@@ -559,7 +403,12 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     if (!fn) return 0;
     const int K = ctx->K, KP = ctx->KP;
     const int KPAD = 2 * LK * J, LN = 32 / LK, W = 8;
-    const int cap = (nmax + LN - 1) / LN * LN;
+    // rows of ids / counts held in shared memory at a time: the longest document of the class, but never more than
+    // keeps two CTAs per SM (longer documents are walked in chunks)
+    const int fixed = 16 + KPAD * 8 + W * KPAD * 8 + align_up(3 * W + 2, 2) * 8 + 256;
+    const int limit = (((int)ctx->prop.sharedMemPerBlockOptin / 2 - fixed) / 12) / (W * LN) * (W * LN);
+    if (limit < W * LN) return fail(ctx, "internal: no shared memory left for the streaming kernel (K=%d)", K);
+    const int cap = std::min((nmax + W * LN - 1) / (W * LN) * (W * LN), limit);
     GroupLayout gl;
     int o = 16 + KPAD * 8;
     gl.off_spart = o; o += W * KPAD * 8;
@@ -567,7 +416,6 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     gl.off_cnt = o;   o += cap * 8;
     gl.off_rid = o;   o += cap * 4;
     gl.bytes = align_up(o, 128);
-    if (gl.bytes > (int)ctx->prop.sharedMemPerBlockOptin / 2) return 0;      // keep two CTAs per SM
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, gl.bytes, 0));
@@ -710,8 +558,8 @@ int launch_estep_sweep(pylda_ctx* ctx, Corpus& cp, const char* mode, int max_ite
 
 int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_stats* st) {
     const int K = ctx->K, KP = ctx->KP;
-    int LK = 0, J = 0, LK1 = 0, J1 = 0;
-    if (!pick_shape(K, &LK, &J, true, 8) || !pick_shape(K, &LK1, &J1, false))
+    int LK = 0, J = 0;
+    if (!pick_shape(K, &LK, &J, true, 8))
         return fail(ctx, "unsupported number of topics K=%d (max 1024)", K);
     const int KPAD = 2 * LK * J;                           // shape of the long-document paths (cluster)
     const int LN = 32 / LK;
@@ -723,7 +571,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     // The hybrid register / shared-memory cluster kernel keeps whole long documents on chip (PYLDA_KERNEL=hybrid).
     // Measured (profiles/r2b_*): its per-trip serial phase (owner sums, exp(psi), cluster exchange) costs what the
     // residency saves -- 73 ms vs 64 ms for the long documents of the headline config -- so streaming stays the default.
-    const bool want_hy = kv && !strcmp(kv, "hybrid");
+    const bool want_hy = kv && (!strcmp(kv, "hybrid") || !strcmp(kv, "cluster"));
     const void* fn_hy = want_hy ? estep_hy_lookup(LK, J, &R_hy) : nullptr;
 
     // Candidate classes, each with a row capacity; a document goes to the class with the smallest
@@ -746,7 +594,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             const GroupLayout g0 = group_layout_v2(c.W, lk, kpad, 0, ST);
             int n = (avail - g0.bytes - 128) / (ST * 8 + 20);
             n = n / ln * ln;
-            const void* fn = lookup_v2(lk, j, c.W, c.W * c.G > 8 ? 1 : 0);
+            const void* fn = lookup_v2(lk, j, c.W, 0);
             if (n > 0 && fn) cls.push_back({0, c.W, c.G, n, lk, j, fn, 0, 0});
         } else if (use_rt) {
             int R = 0;
@@ -777,9 +625,6 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     long long nlong = NC ? cls[0].lo : D;          // documents [0, nlong) fit no single-CTA class
     ClassTimer timer;
     long long nstream = nlong;
-    // The cluster path is correct (parity tests run it with PYLDA_KERNEL=cluster) but at 8 warps per SM
-    // its per-trip serial phase (cluster barrier + exp(psi) + reductions) still costs more than
-    // re-streaming from L2; it stays opt-in until that phase is shortened.
     if (nlong > 0 && fn_hy) {
         // hybrid register / shared-memory tile kernel: clusters of C = 1, 2, 4, 8 CTAs, carved from the short end
         const int capr = 8 * LN * R_hy;
@@ -840,80 +685,14 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         }
         nstream = hi;
     }
-    const void* fn_cl = (kv && !strcmp(kv, "cluster")) ? estep_cl_lookup(LK, J) : nullptr;
-    if (nlong > 0 && fn_cl) {
-        // cluster classes: C CTAs per document, each CTA keeps a slice of at most cap_cl rows resident
-        const GroupLayout g0 = group_layout_cl(KPAD, 0, ST);
-        int cap_cl = (smem_budget - g0.bytes - 128) / (ST * 8 + 20);
-        cap_cl = cap_cl / LN * LN;
-        if (cap_cl >= LN) {
-            const GroupLayout gl = group_layout_cl(KPAD, cap_cl, ST);
-            CK(cudaFuncSetAttribute(fn_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.bytes));
-            CK(cudaMemsetAsync(cp.docterm, 0, (size_t)std::max<long long>(D, 1) * sizeof(double), ctx->stream));
-            long long hi = nlong;                   // classes are carved from the short end of [0, nlong)
-            for (int C = 2; C <= 8 && hi > 0; C <<= 1) {
-                const long long lo = first_leq(C * cap_cl);      // documents [lo, hi) have n <= C * cap_cl
-                if (lo >= hi) continue;
-                const long long nd = hi - lo;
-                cudaLaunchConfig_t cfg;
-                memset(&cfg, 0, sizeof cfg);
-                cfg.blockDim = dim3(256);
-                cfg.dynamicSmemBytes = (size_t)gl.bytes;
-                cfg.stream = ctx->stream;
-                cudaLaunchAttribute attr;
-                attr.id = cudaLaunchAttributeClusterDimension;
-                attr.val.clusterDim.x = C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-                cfg.attrs = &attr; cfg.numAttrs = 1;
-                cfg.gridDim = dim3((unsigned)(C * ctx->prop.multiProcessorCount));
-                int ncl = 0;
-                CK(cudaOccupancyMaxActiveClusters(&ncl, fn_cl, &cfg));
-                if (ncl < 1) break;                 // this cluster size cannot be scheduled: leave the rest to streaming
-                ncl = (int)std::min<long long>(ncl, nd);
-                cfg.gridDim = dim3((unsigned)(ncl * C));
-                EParams p;
-                memset(&p, 0, sizeof p);
-                p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
-                p.order = cp.order + lo; p.ndocs = (int)nd; p.counter = nullptr;
-                p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.alpha_max = ctx->alpha_max;
-                p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.docterm = cp.docterm; p.iters = cp.iters;
-                p.K = K; p.KP = KP; p.ST = ST; p.max_iter = max_iter; p.tol = tol;
-                p.W = 8; p.nmax = cap_cl; p.group_bytes = gl.bytes; p.off_groups = 0;
-                p.off_gam = gl.off_gam; p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt;
-                p.off_mwr = gl.off_mwr; p.off_rid = gl.off_rid; p.off_tile = gl.off_tile;
-                void* args[] = {&p};
-                timer.begin(ctx->stream, "cluster C=%d docs=%lld nmax=%d nmin=%d smem=%d clusters=%d", C, nd, ns[lo],
-                            ns[hi - 1], gl.bytes, ncl);
-                CK(cudaLaunchKernelExC(&cfg, fn_cl, args));
-                timer.end(ctx->stream);
-                st->n_launches++;
-                st->n_estep_launches++;
-                hi = lo;
-            }
-            nstream = hi;
-        }
-    }
     st->docs_streamed = nstream;
     st->docs_resident = D - nstream;
     if (nstream > 0) {
-        // second-generation streaming kernel for everything whose ids/counts fit its shared memory
-        // (n up to ~9000 terms); the first-generation one remains for pathologically long documents
-        long long s2_lo = nstream;
-        if (!(kv && !strcmp(kv, "stream1"))) {
-            const int limit = ((int)ctx->prop.sharedMemPerBlockOptin / 2 - 16 - 2 * LK * J * 8 * 9 - 512) / 12;
-            s2_lo = first_leq(limit);
-            if (s2_lo < nstream) {
-                int launched = 0;
-                timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream - s2_lo, ns[s2_lo]);
-                if (launch_stream2(ctx, cp, s2_lo, nstream, ns[s2_lo], LK, J, max_iter, tol, st, 15, &launched, pc.nc)) return 1;
-                timer.end(ctx->stream);
-                if (!launched) s2_lo = nstream;
-            }
-        }
-        if (s2_lo > 0) {
-            timer.begin(ctx->stream, "streaming docs=%lld nmax=%d", s2_lo, ns[0]);
-            if (launch_streaming(ctx, cp, s2_lo, LK1, J1, max_iter, tol, st, 0)) return 1;
-            timer.end(ctx->stream);
-        }
+        int launched = 0;
+        timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream, ns[0]);
+        if (launch_stream2(ctx, cp, 0, nstream, ns[0], LK, J, max_iter, tol, st, 15, &launched, pc.nc)) return 1;
+        timer.end(ctx->stream);
+        if (!launched) return fail(ctx, "no streaming kernel instantiation for LK=%d J=%d", LK, J);
     }
     for (int ci = 0; ci < NC; ++ci) {
         const Cls& c = cls[ci];
@@ -1216,8 +995,8 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
         const char* kv = getenv("PYLDA_KERNEL");
         const char* pv = getenv("PYLDA_PRECISION");
         const int rc = (pv && *pv && strcmp(pv, "f64")) ? launch_estep_sweep(ctx, cp, pv, max_iter, tol, &st)
-                       : (kv && !strcmp(kv, "v1"))      ? launch_estep_v1(ctx, cp, max_iter, tol, &st)
                                                         : launch_estep(ctx, cp, max_iter, tol, &st);
+        (void)kv;
         if (rc) return 1;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));

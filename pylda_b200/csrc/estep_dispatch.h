@@ -1,12 +1,6 @@
 // Kernel lookup: one translation unit per LK so the instantiations compile in parallel.
 #pragma once
 namespace pylda {
-const void* estep_kernel_lk1(int J, bool resident);
-const void* estep_kernel_lk2(int J, bool resident);
-const void* estep_kernel_lk4(int J, bool resident);
-const void* estep_kernel_lk8(int J, bool resident);
-const void* estep_kernel_lk16(int J, bool resident);
-const void* estep_kernel_lk32(int J, bool resident);
 // second generation (estep_v2.cuh): W = warps per document group (1, 2, 4, 8); V = 1: 16-warp CTAs
 const void* estep_v2_lk1(int J, int W, int V);
 const void* estep_v2_lk2(int J, int W, int V);
@@ -22,8 +16,6 @@ const void* estep_rt_lk4(int J, int W, int R, int NWARPS, int* rows_per_lane);
 const void* estep_rt_lk8(int J, int W, int R, int NWARPS, int* rows_per_lane);
 const void* estep_rt_lk16(int J, int W, int R, int NWARPS, int* rows_per_lane);
 const void* estep_rt_lk32(int J, int W, int R, int NWARPS, int* rows_per_lane);
-// cluster generation (estep_cl.cuh): one long document per thread-block cluster of 2, 4 or 8 CTAs
-const void* estep_cl_lookup(int LK, int J);
 // second-generation streaming kernel (documents longer than every resident class)
 const void* estep_stream_lookup(int LK, int J);
 // hybrid register / shared-memory tile kernel for long documents (estep_hy.cuh), clusters of 1, 2, 4, 8 CTAs

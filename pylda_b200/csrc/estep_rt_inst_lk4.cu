@@ -21,10 +21,6 @@ const void* estep_rt_lk4(int J, int W, int R, int NWARPS, int* rows_per_lane) {
 #undef PYLDA_CASE
 #undef PYLDA_CASE_W
     *rows_per_lane = R;
-    // more warps per SM with fewer rows per lane (K ~ 100 shapes; tuning set)
-#define PYLDA_ALT(JJ, WW, RR, NW) if (J == JJ && W == WW && R == RR && NWARPS == NW) return (const void*)estep_rt<LK, JJ, WW, RR, NW>;
-    PYLDA_ALT(13, 2, 2, 10) PYLDA_ALT(13, 1, 2, 10) PYLDA_ALT(13, 2, 1, 16) PYLDA_ALT(13, 4, 1, 16) PYLDA_ALT(13, 4, 2, 12)
-#undef PYLDA_ALT
     return nullptr;
 }
 }  // namespace pylda

@@ -20,12 +20,6 @@ const void* estep_rt_lk8(int J, int W, int R, int NWARPS, int* rows_per_lane) {
 #undef PYLDA_CASE
 #undef PYLDA_CASE_W
     *rows_per_lane = R;
-    // more warps per SM with fewer rows per lane (K ~ 100 shapes; tuning set)
-#define PYLDA_ALT(JJ, WW, RR, NW) if (J == JJ && W == WW && R == RR && NWARPS == NW) return (const void*)estep_rt<LK, JJ, WW, RR, NW>;
-    PYLDA_ALT(7, 1, 3, 12) PYLDA_ALT(7, 2, 3, 12) PYLDA_ALT(7, 4, 3, 12)
-    PYLDA_ALT(7, 1, 2, 16) PYLDA_ALT(7, 2, 2, 16) PYLDA_ALT(7, 4, 2, 16)
-    PYLDA_ALT(7, 2, 4, 10)
-#undef PYLDA_ALT
     return nullptr;
 }
 }  // namespace pylda

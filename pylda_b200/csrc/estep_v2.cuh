@@ -442,17 +442,24 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         if (gt == 0) nxt = atomicAdd(p.counter, 1);
         const int d = p.order[idx];
         const long long base = p.row_ptr[d];
-        const int n = (int)(p.row_ptr[d + 1] - base);       // host guarantees n <= p.nmax
+        const int n = (int)(p.row_ptr[d + 1] - base);
         const int npad = (n + LN - 1) / LN * LN;
-        const int NG = npad / LN;
+        // ids and counts live in shared memory, p.nmax rows at a time: a document longer than that (thousands of
+        // terms) is walked in chunks that are re-staged every trip -- 12 bytes per row against the 8 K of its B row
+        const int cap = p.nmax;                             // multiple of W * LN
+        const int nch = (npad + cap - 1) / cap;
+        auto stage = [&](int ch) {
+            const int r0 = ch * cap, rows = min(cap, npad - r0);
+            for (int r = gt; r < rows; r += GT) {
+                const bool real = r0 + r < n;
+                rid[r] = p.ids[base + (real ? r0 + r : 0)];     // pad rows: a valid row with weight 0
+                cnt[r] = real ? (double)p.cts[base + r0 + r] : 0.0;
+            }
+            return rows;
+        };
         int csum = 0;
-        for (int r = gt; r < npad; r += GT) {
-            const bool real = r < n;
-            rid[r] = p.ids[base + (real ? r : 0)];          // pad rows: a valid row with weight 0
-            const int c = real ? p.cts[base + r] : 0;
-            cnt[r] = (double)c;
-            csum += c;
-        }
+        for (int r = gt; r < n; r += GT) csum += p.cts[base + r];
+        int rows_c = stage(0);
         csum = __reduce_add_sync(0xffffffffu, csum);
         if (lane == 0) red[gw] = (double)csum;
         __syncthreads();
@@ -489,7 +496,13 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
             double s[2 * J];
 #pragma unroll
             for (int i = 0; i < 2 * J; ++i) s[i] = 0.0;
-            {
+            for (int ch = 0; ch < nch; ++ch) {
+                if (nch > 1) {
+                    __syncthreads();
+                    rows_c = stage(ch);
+                    __syncthreads();
+                }
+                const int NG = rows_c / LN;
                 // the warp's row groups gw, gw + W, ...: forwards on even trips, backwards on odd ones, so that the
                 // rows read last are read first again and the L1 cache (a fraction of the tile) is not swept
                 // cyclically -- every trip gets ~L1/tile of its rows from L1 instead of none
@@ -617,21 +630,29 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
 
         // ---- final pass: phi from the LAST e, scattered with red.global.add.f64 -----------------
         double lacc = 0.0;
-        for (int r0 = gw * LN; r0 < n; r0 += W * LN) {
-            const int r = r0 + nl;
-            const bool ok = r < n;
-            const int id = rid[r];
-            double b[2 * J];
-            const double part = row_dot<LK, J>(p.Bt + (size_t)id * KP + 2 * kl, e, b);
-            const double c = cnt[r];
-            const double w = ok ? c * rcp_nr(part) : 0.0;
-            if (ok && kl == 0) lacc = fma(c, p.mw[id] + log(part), lacc);
-            double* dst = p.phi_ss + (size_t)id * KP + 2 * kl;
+        for (int ch = 0; ch < nch; ++ch) {
+            if (nch > 1) {
+                __syncthreads();
+                rows_c = stage(ch);
+                __syncthreads();
+            }
+            const int rbase = ch * cap;
+            for (int r0 = gw * LN; r0 < rows_c; r0 += W * LN) {
+                const int r = r0 + nl;
+                const bool ok = rbase + r < n;
+                const int id = rid[r];
+                double b[2 * J];
+                const double part = row_dot<LK, J>(p.Bt + (size_t)id * KP + 2 * kl, e, b);
+                const double c = cnt[r];
+                const double w = ok ? c * rcp_nr(part) : 0.0;
+                if (ok && kl == 0) lacc = fma(c, p.mw[id] + log(part), lacc);
+                double* dst = p.phi_ss + (size_t)id * KP + 2 * kl;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                if (ok && kl + LK * j < KP2) {
-                    atomicAdd(dst + 2 * LK * j, w * b[2 * j] * e[2 * j]);                       // :207
-                    if (2 * (kl + LK * j) + 1 < K) atomicAdd(dst + 2 * LK * j + 1, w * b[2 * j + 1] * e[2 * j + 1]);
+                for (int j = 0; j < J; ++j) {
+                    if (ok && kl + LK * j < KP2) {
+                        atomicAdd(dst + 2 * LK * j, w * b[2 * j] * e[2 * j]);                       // :207
+                        if (2 * (kl + LK * j) + 1 < K) atomicAdd(dst + 2 * LK * j + 1, w * b[2 * j + 1] * e[2 * j + 1]);
+                    }
                 }
             }
         }

@@ -8,9 +8,8 @@ const void* estep_v2_lk8(int J, int W, int V) {
 #define PYLDA_CASE_W(JJ, WW) \
     if constexpr (2 * LK * JJ <= 128 * WW) {                                                        \
         if (J == JJ && W == WW && V == 0) return (const void*)estep_v2<LK, JJ, WW, 0>;              \
-        if constexpr (WW > 1) { if (J == JJ && W == WW && V == 1) return (const void*)estep_v2<LK, JJ, WW, 1>; } \
     }
-#define PYLDA_CASE(JJ) PYLDA_CASE_W(JJ, 1) PYLDA_CASE_W(JJ, 2) PYLDA_CASE_W(JJ, 4) PYLDA_CASE_W(JJ, 8)
+#define PYLDA_CASE(JJ) PYLDA_CASE_W(JJ, 8)      // the one class in use (8 warps per document); others were tuning variants
     PYLDA_CASE(5)
     PYLDA_CASE(7)
     PYLDA_CASE(8)

@@ -74,10 +74,10 @@ def test_against_oracle_shapes(ctx, K, V, D, length):
     print("stats", out["stats"])
 
 
-@pytest.mark.parametrize("kernel", ["v1", "v2", "cluster", "default"])
+@pytest.mark.parametrize("kernel", ["v2", "hybrid", "default"])
 def test_every_kernel_generation_matches_oracle(ctx, kernel, monkeypatch):
-    """The library holds four generations of the per-document kernel (first, shared-memory tile,
-    register tile [default], thread-block cluster for long documents); PYLDA_KERNEL selects one.
+    """The library holds several per-document kernels (shared-memory tile, register tile + narrow stages + streaming
+    [default], hybrid register / shared-memory thread-block cluster for long documents); PYLDA_KERNEL selects one.
     All of them must agree with the oracle on a corpus with short, medium and very long documents."""
     from oracle import estep_oracle as O
     from pylda_b200 import synthetic
@@ -274,8 +274,8 @@ def test_random_shapes_sweep(ctx, seed):
 
 
 def test_pathologically_long_document(ctx):
-    """A document with more distinct terms than the streaming kernel can index from shared memory
-    (~9000) falls back to the first-generation streaming kernel; same results."""
+    """A document with more distinct terms than the streaming kernel holds in shared memory at a time (~9000) is
+    walked in chunks, re-staged every trip; same results."""
     from oracle import estep_oracle as O
     from pylda_b200 import synthetic
     K, V = 8, 16000
@@ -294,7 +294,6 @@ def test_pathologically_long_document(ctx):
     out = ctx.estep(0, eta, alpha, 50, 1e-6)
     _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "long document")
     assert out["stats"]["docs_streamed"] >= 1
-    assert out["stats"]["n_estep_launches"] >= 2
 
 
 def test_dead_topic_elimination_changes_nothing(ctx, monkeypatch):
