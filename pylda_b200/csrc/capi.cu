@@ -126,7 +126,7 @@ struct pylda_ctx {
     double* scal = nullptr;      // 8 doubles
     double* partial = nullptr;   // reduction scratch
     size_t partial_cap = 0;
-    int* counters = nullptr;     // class queue heads
+    int* counters = nullptr;     // 32 ints: class queue heads [1..13), revived documents [14], long-document kernels [16..19)
     int* park_ctr = nullptr;     // narrow stages: list lengths [0..16) and queue heads [16..32)
     double* e_dead = nullptr;    // (K,) exp(psi(alpha_k))
     double* wsum = nullptr;      // (V,) row weights of the documents finished by the narrow stages
@@ -399,8 +399,6 @@ struct ClassTimer {
 int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int nmax, int LK, int J, int max_iter,
                    double tol, pylda_stats* st, int counter_slot, int* launched, int park_nc) {
     *launched = 0;
-    const void* fn = estep_stream_lookup(LK, J);
-    if (!fn) return 0;
     const int K = ctx->K, KP = ctx->KP;
     const int KPAD = 2 * LK * J, LN = 32 / LK, W = 8;
     // rows of ids / counts held in shared memory at a time: the longest document of the class, but never more than
@@ -409,6 +407,11 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     const int limit = (((int)ctx->prop.sharedMemPerBlockOptin / 2 - fixed) / 12) / (W * LN) * (W * LN);
     if (limit < W * LN) return fail(ctx, "internal: no shared memory left for the streaming kernel (K=%d)", K);
     const int cap = std::min((nmax + W * LN - 1) / (W * LN) * (W * LN), limit);
+    // lean instantiation when no document of the class can be handed over (all longer than 192 terms) or chunked
+    const int nmin = cp.n_sorted[(size_t)hi - 1];
+    const bool full = (park_nc > 0 && nmin <= 192) || nmax > cap;
+    const void* fn = estep_stream_lookup(LK, J, full);
+    if (!fn) return 0;
     GroupLayout gl;
     int o = 16 + KPAD * 8;
     gl.off_spart = o; o += W * KPAD * 8;
@@ -617,7 +620,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     auto first_leq = [&](int limit) -> long long {   // first index (descending order) whose n <= limit
         return std::partition_point(ns.begin(), ns.end(), [&](int n) { return n > limit; }) - ns.begin();
     };
-    CK(cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters, 0, 32 * sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(ctx->park_ctr, 0, PARK_CTRS * sizeof(int), ctx->stream));
     const ParkCfg pc = park_config(ctx);
     for (int i = 0; i < NC; ++i) cls[i].lo = first_leq(cls[i].cap);
@@ -688,9 +691,13 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     st->docs_streamed = nstream;
     st->docs_resident = D - nstream;
     if (nstream > 0) {
+        // Long documents: the streaming kernel.  (Tried in round 2 and dropped, both measured slower at the headline
+        // config -- DESIGN.md section 6: a cluster kernel with the whole tile on chip [estep_hy, kept opt-in], and a
+        // 16-warp streaming kernel with a resident shared-memory prefix: streaming is bound by the bytes it keeps in
+        // flight towards L2, and one document per SM keeps fewer in flight than two.)
         int launched = 0;
         timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream, ns[0]);
-        if (launch_stream2(ctx, cp, 0, nstream, ns[0], LK, J, max_iter, tol, st, 15, &launched, pc.nc)) return 1;
+        if (launch_stream2(ctx, cp, 0, nstream, ns[0], LK, J, max_iter, tol, st, 17, &launched, pc.nc)) return 1;
         timer.end(ctx->stream);
         if (!launched) return fail(ctx, "no streaming kernel instantiation for LK=%d J=%d", LK, J);
     }
@@ -806,8 +813,8 @@ int pylda_create(pylda_ctx** out, int device) {
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     cudaMalloc((void**)&ctx->scal, 8 * sizeof(double));
     cudaMemset(ctx->scal, 0, 8 * sizeof(double));
-    cudaMalloc((void**)&ctx->counters, 16 * sizeof(int));
-    cudaMemset(ctx->counters, 0, 16 * sizeof(int));
+    cudaMalloc((void**)&ctx->counters, 32 * sizeof(int));
+    cudaMemset(ctx->counters, 0, 32 * sizeof(int));
     cudaMalloc((void**)&ctx->park_ctr, PARK_CTRS * sizeof(int));
     cudaMemset(ctx->park_ctr, 0, PARK_CTRS * sizeof(int));
     *out = ctx;

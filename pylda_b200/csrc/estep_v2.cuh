@@ -393,7 +393,10 @@ __device__ __forceinline__ void rows_accum_global(const double* __restrict__ Bt,
     }
 }
 
-template <int LK, int J>
+// FULL = false: lean instantiation for classes whose documents can neither be handed over to the narrow stages
+// (all longer than 192 terms) nor need chunked staging -- the long documents of the headline config; the extra
+// live state of those two features costs the 128-register kernel spills in its trip loop.
+template <int LK, int J, bool FULL>
 __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
     constexpr int W = 8;
     constexpr int LN = 32 / LK;
@@ -447,19 +450,22 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         // ids and counts live in shared memory, p.nmax rows at a time: a document longer than that (thousands of
         // terms) is walked in chunks that are re-staged every trip -- 12 bytes per row against the 8 K of its B row
         const int cap = p.nmax;                             // multiple of W * LN
-        const int nch = (npad + cap - 1) / cap;
-        auto stage = [&](int ch) {
-            const int r0 = ch * cap, rows = min(cap, npad - r0);
-            for (int r = gt; r < rows; r += GT) {
-                const bool real = r0 + r < n;
-                rid[r] = p.ids[base + (real ? r0 + r : 0)];     // pad rows: a valid row with weight 0
-                cnt[r] = real ? (double)p.cts[base + r0 + r] : 0.0;
-            }
-            return rows;
-        };
+        const int nch = FULL ? (npad + cap - 1) / cap : 1;
+        // (a macro, not a lambda: by-reference captures put the captured variables on the stack)
+#define PYLDA_STAGE_CHUNK(CH)                                                                          \
+        {                                                                                              \
+            const int r0_ = (CH) * cap;                                                                \
+            rows_c = min(cap, npad - r0_);                                                             \
+            for (int r = gt; r < rows_c; r += GT) {                                                    \
+                const bool real = r0_ + r < n;                                                         \
+                rid[r] = p.ids[base + (real ? r0_ + r : 0)];     /* pad rows: a valid row, weight 0 */ \
+                cnt[r] = real ? (double)p.cts[base + r0_ + r] : 0.0;                                   \
+            }                                                                                          \
+        }
         int csum = 0;
         for (int r = gt; r < n; r += GT) csum += p.cts[base + r];
-        int rows_c = stage(0);
+        int rows_c;
+        PYLDA_STAGE_CHUNK(0)
         csum = __reduce_add_sync(0xffffffffu, csum);
         if (lane == 0) red[gw] = (double)csum;
         __syncthreads();
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         int it = 0;
         const double tolK = p.tol * (double)K;
         // hand-over threshold of this document: 32 live topics for n <= 96, 16 for n <= 192, never above
-        const int park_thr = (p.park_nc >= 16 && n <= 96) ? 32 : (p.park_nc > 0 && n <= 192) ? p.park_nc : 0;
+        const int park_thr = !FULL ? 0 : (p.park_nc >= 16 && n <= 96) ? 32 : (p.park_nc > 0 && n <= 192) ? p.park_nc : 0;
         bool parked = false;
         while (true) {
 #pragma unroll
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
             for (int ch = 0; ch < nch; ++ch) {
                 if (nch > 1) {
                     __syncthreads();
-                    rows_c = stage(ch);
+                    PYLDA_STAGE_CHUNK(ch)
                     __syncthreads();
                 }
                 const int NG = rows_c / LN;
@@ -578,7 +584,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
 #pragma unroll
             for (int w = 0; w < W; ++w) dsum += red[w];
             if (dsum <= tolK || it >= p.max_iter) break;                  // :189-190 / :174
-            if (park_thr > 0) {
+            if (FULL && park_thr > 0) {
                 // Few enough topics alive (gamma_k != alpha_k): the narrow stages (estep_narrow.cuh) finish the
                 // document.  This kernel has no compact stage of its own, so it hands over at 32 live topics already.
                 unsigned bal[U];
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         for (int ch = 0; ch < nch; ++ch) {
             if (nch > 1) {
                 __syncthreads();
-                rows_c = stage(ch);
+                PYLDA_STAGE_CHUNK(ch)
                 __syncthreads();
             }
             const int rbase = ch * cap;
@@ -690,5 +696,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         }
     }
 }
+
+#undef PYLDA_STAGE_CHUNK
 
 }  // namespace pylda
