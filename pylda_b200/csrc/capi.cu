@@ -318,15 +318,24 @@ int ensure_partial(pylda_ctx* ctx, size_t n) {
     return 0;
 }
 
+// psisum[k] = psi(sum_v eta_kv), rowsum[k] = sum_v eta_kv (scratch when the caller does not need it)
+int rowsum_psi(pylda_ctx* ctx, const double* eta, int K, int V, double* psisum, double* rowsum) {
+    const int chunks = std::max(1, std::min(64, (4 * ctx->prop.multiProcessorCount + K - 1) / K));
+    if (ensure_partial(ctx, (size_t)K * chunks)) return 1;
+    k_rowsum<<<dim3(K, chunks), 256, 0, ctx->stream>>>(eta, K, V, ctx->partial);
+    k_psi_of_rowsum<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial, K, chunks, psisum, rowsum);
+    return 0;
+}
+
 int prepare_tables(pylda_ctx* ctx, bool heldout, int* launches) {
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;
     double* psisum = ctx->kbuf;
-    k_rowsum_psi<<<K, 256, 0, ctx->stream>>>(ctx->eta, K, V, psisum, ctx->kbuf + K);
+    if (rowsum_psi(ctx, ctx->eta, K, V, psisum, ctx->kbuf + K)) return 1;
     dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
     k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(ctx->eta, psisum, K, V, KP, ctx->Elt);
     const int nb = std::min((V + 7) / 8, ctx->prop.multiProcessorCount * 8);
     k_build_B<<<nb, 256, 0, ctx->stream>>>(ctx->Elt, K, V, KP, ctx->Bt, ctx->mw, ctx->phi);
-    *launches += 3;
+    *launches += 4;
     if (heldout) {
         const int nchunk = 64;
         if (ensure_partial(ctx, (size_t)2 * nchunk * K)) return 1;
@@ -942,7 +951,6 @@ int pylda_set_model(pylda_ctx* ctx, int K, int V, const double* eta_KxV, const d
         CK(cudaMemsetAsync(ctx->Bt + vkp, 0, 1024 * sizeof(double), ctx->stream));
         CK(dalloc(&ctx->mw, (size_t)V));
         CK(dalloc(&ctx->phi, vkp));
-        CK(dalloc(&ctx->phi_KV, kv));
         CK(dalloc(&ctx->kbuf, (size_t)4 * K));
         CK(dalloc(&ctx->alpha_ss, (size_t)K));
         CK(dalloc(&ctx->e_dead, (size_t)K));
@@ -1110,6 +1118,7 @@ int pylda_get_results(pylda_ctx* ctx, int slot, double* gamma_DxK, double* phi_s
         CK(cudaMemcpyAsync(gamma_DxK, cp.gamma, (size_t)cp.D * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (phi_ss_KxV) {
+        if (!ctx->phi_KV) CK(dalloc(&ctx->phi_KV, (size_t)K * V));      // (K, V) copy: only when the caller asks for phi_ss
         if (!ctx->phi_KV_valid) {
             dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
             k_transpose_VK_to_KV<<<tg, tb, 0, ctx->stream>>>(ctx->phi, K, V, KP, ctx->phi_KV);
@@ -1159,13 +1168,15 @@ int pylda_mstep_resident(pylda_ctx* ctx, double alpha_beta, double* topic_ll, do
     if (!(alpha_beta > 0.0)) return fail(ctx, "pylda_mstep_resident: alpha_beta must be > 0");
     CK(cudaSetDevice(ctx->device));
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;
-    if (!ctx->phi_KV_valid) {
-        dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
-        k_transpose_VK_to_KV<<<tg, tb, 0, ctx->stream>>>(ctx->phi, K, V, KP, ctx->phi_KV);
-        ctx->phi_KV_valid = true;
-    }
+    // straight from the (V, KP) statistics (no (K, V) copy of them, no transpose); scratch: 2 K doubles
     double* rowterm = ctx->kbuf + 3 * K;
-    k_mstep<<<K, 256, 0, ctx->stream>>>(ctx->eta, ctx->phi_KV, K, V, alpha_beta, rowterm);
+    {
+        const int kt = (K + 31) / 32;
+        const int chunks = std::max(1, std::min((V + 31) / 32, (8 * ctx->prop.multiProcessorCount + kt - 1) / kt));
+        if (ensure_partial(ctx, (size_t)2 * K * chunks)) return 1;
+        k_mstep_tiled<<<dim3(chunks, kt), dim3(32, 8), 0, ctx->stream>>>(ctx->eta, ctx->phi, K, V, KP, alpha_beta, ctx->partial);
+        k_mstep_final<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->partial, K, chunks, rowterm);
+    }
     CK(cudaGetLastError());
     std::vector<double> rt((size_t)K);
     CK(cudaMemcpyAsync(rt.data(), rowterm, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1195,7 +1206,7 @@ int pylda_top_words(pylda_ctx* ctx, int top, int32_t* idx_KxT, double* prob_KxT)
     CK(cudaSetDevice(ctx->device));
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;
     // E_log_eta of the CURRENT eta and its per-topic logsumexp (the statistics accumulator is left alone)
-    k_rowsum_psi<<<K, 256, 0, ctx->stream>>>(ctx->eta, K, V, ctx->kbuf, ctx->kbuf + K);
+    if (rowsum_psi(ctx, ctx->eta, K, V, ctx->kbuf, ctx->kbuf + K)) return 1;
     dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
     k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(ctx->eta, ctx->kbuf, K, V, KP, ctx->Elt);
     const int nchunk = 64;
@@ -1218,11 +1229,11 @@ int pylda_dirichlet_expectation(pylda_ctx* ctx, int K, int V, const double* eta_
     double *eta = nullptr, *ps = nullptr, *elt = nullptr, *out = nullptr;
     const int KP = (K + 1) & ~1;
     CK(dalloc(&eta, (size_t)K * V));
-    CK(dalloc(&ps, (size_t)K));
+    CK(dalloc(&ps, (size_t)2 * K));
     CK(dalloc(&elt, (size_t)V * KP));
     CK(dalloc(&out, (size_t)K * V));
     CK(cudaMemcpyAsync(eta, eta_KxV, (size_t)K * V * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    k_rowsum_psi<<<K, 256, 0, ctx->stream>>>(eta, K, V, ps, nullptr);
+    if (rowsum_psi(ctx, eta, K, V, ps, nullptr)) return 1;
     dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
     k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(eta, ps, K, V, KP, elt);
     k_transpose_VK_to_KV<<<tg, tb, 0, ctx->stream>>>(elt, K, V, KP, out);

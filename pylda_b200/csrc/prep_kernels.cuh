@@ -24,20 +24,31 @@ __device__ __forceinline__ double block_sum(double v, double* sh /* >= 32 double
 }
 
 // psisum[k] = psi(sum_v eta[k][v])                                  (inferencer.py:18)
-__global__ void k_rowsum_psi(const double* __restrict__ eta, int K, int V, double* psisum, double* rowsum) {
+// row sums of eta (K, V): grid (K, chunks of V) so that small K still fills the machine; the partial sums go to
+// part[k * chunks + c] and k_psi_of_rowsum adds them in a fixed order (bit-reproducible from call to call) and turns
+// them into psi(sum_v eta_kv) (inferencer.py:18)
+__global__ void k_rowsum(const double* __restrict__ eta, int K, int V, double* __restrict__ part) {
     __shared__ double sh[32];
     const int k = blockIdx.x;
+    const int per = (V + gridDim.y - 1) / gridDim.y;
+    const int v0 = blockIdx.y * per, v1 = min(V, v0 + per);
     const double* row = eta + (size_t)k * V;
     double a = 0.0;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) a += row[v];
+    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) a += row[v];
     a = block_sum(a, sh);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) part[(size_t)k * gridDim.y + blockIdx.y] = a;
+}
+__global__ void k_psi_of_rowsum(const double* __restrict__ part, int K, int chunks, double* __restrict__ psisum,
+                                double* __restrict__ rowsum) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) {
+        double a = 0.0;
+        for (int c = 0; c < chunks; ++c) a += part[(size_t)k * chunks + c];
         psisum[k] = digamma_pos(a);
         if (rowsum) rowsum[k] = a;
     }
 }
 
-// Elt[v][k] = psi(eta[k][v]) - psisum[k], transposed to (V, KP)     (inferencer.py:18)
 __global__ void k_elog_transpose(const double* __restrict__ eta, const double* __restrict__ psisum, int K, int V,
                                  int KP, double* __restrict__ Elt) {
     __shared__ double t[32][33];
@@ -210,22 +221,59 @@ __global__ void k_alpha_ss(const double* __restrict__ gamma, long long D, int K,
 // Device M-step (variational_bayes.py:222-226), one block per topic row:
 // rowterm[k] = sum_v lgamma(eta_kv) - lgamma(sum_v eta_kv) from the OLD eta, then
 // eta_kv <- phi_KV[k][v] + alpha_beta.
-__global__ void k_mstep(double* __restrict__ eta, const double* __restrict__ phi_KV, int K, int V, double alpha_beta,
-                        double* rowterm) {
-    __shared__ double sh[32];
-    const int k = blockIdx.x;
-    double* row = eta + (size_t)k * V;
-    const double* prow = phi_KV + (size_t)k * V;
-    double a = 0.0, s = 0.0;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) {
-        const double x = row[v];
-        a += lgamma(x);
-        s += x;
-        row[v] = prow[v] + alpha_beta;
+// Device M-step (variational_bayes.py:222-226) straight from the (V, KP) statistics: a 32 x 32 tile of phi is read
+// along k, turned through shared memory, and meets the (K, V) rows of eta along v -- no (K, V) copy of the
+// statistics.  Grid (chunks of V, K / 32): a block walks the tiles of its V-chunk and leaves, per topic,
+// part[k * chunks + c] = sum_v lgamma(eta_old) and part[(K + k) * chunks + c] = sum_v eta_old over the chunk;
+// k_mstep_final adds the chunks in a fixed order.  eta <- phi + alpha_beta.
+__global__ void k_mstep_tiled(double* __restrict__ eta, const double* __restrict__ phi, int K, int V, int KP, double alpha_beta,
+                              double* __restrict__ part) {
+    __shared__ double tile[32][33];
+    const int chunks = gridDim.x;
+    const int tiles = (V + 31) / 32, per = (tiles + chunks - 1) / chunks;
+    const int k0 = blockIdx.y * 32;
+    double lg[4] = {0.0, 0.0, 0.0, 0.0}, sm[4] = {0.0, 0.0, 0.0, 0.0};      // blockDim = (32, 8): 4 topics per thread
+    for (int t = blockIdx.x * per; t < min(tiles, (int)(blockIdx.x + 1) * per); ++t) {
+        const int v0 = t * 32;
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += 8) {                       // rows of the tile = words
+            const int v = v0 + i, k = k0 + threadIdx.x;
+            tile[i][threadIdx.x] = (v < V && k < K) ? phi[(size_t)v * KP + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                     // rows of the result = topics
+            const int i = threadIdx.y + 8 * q;
+            const int k = k0 + i, v = v0 + threadIdx.x;
+            if (k < K && v < V) {
+                const size_t o = (size_t)k * V + v;
+                const double x = eta[o];
+                lg[q] += lgamma(x);
+                sm[q] += x;
+                eta[o] = tile[threadIdx.x][i] + alpha_beta;
+            }
+        }
     }
-    a = block_sum(a, sh);
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) rowterm[k] = a - lgamma(s);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + threadIdx.y + 8 * q;
+        const double a = warp_sum(lg[q]), b = warp_sum(sm[q]);
+        if (threadIdx.x == 0 && k < K) {
+            part[(size_t)k * chunks + blockIdx.x] = a;
+            part[(size_t)(K + k) * chunks + blockIdx.x] = b;
+        }
+    }
+}
+__global__ void k_mstep_final(const double* __restrict__ part, int K, int chunks, double* __restrict__ rowterm) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) {
+        double a = 0.0, b = 0.0;
+        for (int c = 0; c < chunks; ++c) {
+            a += part[(size_t)k * chunks + c];
+            b += part[(size_t)(K + k) * chunks + c];
+        }
+        rowterm[k] = a - lgamma(b);
+    }
 }
 
 __global__ void k_special(int which, long long n, const double* __restrict__ x, double* __restrict__ out) {

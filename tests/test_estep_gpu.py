@@ -270,7 +270,8 @@ def test_random_shapes_sweep(ctx, seed):
     _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "seed=%d K=%d V=%d D=%d" % (seed, K, V, D))
     assert abs(out["words_ll"] - ref["words_ll"]) <= RTOL * abs(ref["words_ll"])
     it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
-    assert numpy.mean(it == ref["iters"]) >= 0.9
+    # trip counts: identical, except that one document sitting on the stop threshold may flip by one trip
+    assert numpy.sum(it != ref["iters"]) <= 1 and numpy.max(numpy.abs(it - ref["iters"])) <= 1
 
 
 def test_pathologically_long_document(ctx):

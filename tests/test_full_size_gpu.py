@@ -100,3 +100,14 @@ def test_config4_full_nips_corpus_fp64(ctx):
     assert abs(out["doc_ll"] - float(g["doc_ll"])) <= RTOL * abs(float(g["doc_ll"]))
     assert numpy.mean(it == g["iters"]) >= 0.999
     print("config 4 full: kernel %.2f ms, mean trips %.1f, stats %s" % (out["stats"]["kernel_ms"], it.mean(), out["stats"]))
+
+
+def test_config5_full_vocabulary_oracle_subsample(ctx):
+    """BASELINE.json configs[4] at its model size -- V = 1M, K = 500 (every V x K table is 4 GB) -- with a reduced
+    number of documents: invariants over the whole run and oracle parity (gamma, trip counts, ELBO) on a subsample
+    that includes the longest and the shortest documents.  Nearly every document is handed from the streaming
+    kernel to the 32- / 16- / 8-column narrow stages on its way."""
+    out = _properties_and_subsample(ctx, 5000, 1000000, 500, "poisson", 1238, 10)
+    st = out["stats"]
+    assert st["docs_narrow"] >= 4500 and st["docs_streamed"] == 5000
+    print("config5 (V=1M) stats", st)
