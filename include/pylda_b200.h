@@ -153,8 +153,9 @@ int pylda_comm_allreduce_sum(pylda_ctx* ctx, double* buf, int64_t n);
 
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister, mapped) so that the H2D/D2H copies of
  * pylda_estep run at full PCIe rate.  Optional: pageable buffers work, only slower.  When the gamma_DxK
- * argument of pylda_estep is page-locked (and alpha_ss_K is NULL) the kernels store gamma directly into
- * it over PCIe while they run, instead of a D x K copy at the end of the call. */
+ * argument of pylda_estep is page-locked, alpha_ss_K is NULL and the hand-over to the narrow stages is off
+ * (alpha too large for topics to die, or PYLDA_PARK=0) the kernels store gamma directly into it over PCIe while
+ * they run, instead of a D x K copy at the end of the call. */
 int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes);
 int pylda_host_unregister(pylda_ctx* ctx, void* ptr);
 

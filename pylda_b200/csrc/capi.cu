@@ -997,7 +997,12 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     memset(&st, 0, sizeof st);
     const int K = ctx->K, V = ctx->V, KP = ctx->KP;
     if (ensure_outputs(ctx, cp)) return 1;
-    cp.gamma_dst = (gamma_host_alias && !want_alpha_ss) ? gamma_host_alias : cp.gamma;
+    // Zero-copy gamma (kernels storing straight into the caller's page-locked buffer) pays off while every kernel
+    // writes whole gamma rows.  With the hand-over to the narrow stages a document's row is written twice and the
+    // second time as scattered 8-byte stores, which cross PCIe one by one (measured: +25 ms per E-step on one GPU,
+    // +136 ms with eight ranks sharing a host): then gamma stays on the device and leaves by one DMA copy.
+    const bool zero_copy = gamma_host_alias && !want_alpha_ss && park_config(ctx).nc == 0;
+    cp.gamma_dst = zero_copy ? gamma_host_alias : cp.gamma;
     cp.gamma_on_device = (cp.gamma_dst == cp.gamma);
     const int nred = ctx->prop.multiProcessorCount * 2;
     const int nass = ctx->prop.multiProcessorCount * 2;

@@ -1,5 +1,6 @@
 #!/bin/bash
-# compute-sanitizer memcheck + racecheck on small E-steps that cover every kernel generation
+# compute-sanitizer memcheck + racecheck on small E-steps that cover every kernel (register tile, narrow stages,
+# shared-memory tile, streaming with hand-over, hybrid cluster kernel), the device M-step and the top-words sort
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
 import os, sys, numpy
@@ -15,13 +16,18 @@ ctx.set_corpus(0, row_ptr, ids, cts)
 for K in (100, 10, 50, 200, 500):
     eta = synthetic.initial_eta(K, V, 1)
     alpha = numpy.full(K, 1.0 / K)
-    for kern in ("default", "v2", "cluster", "v1"):
+    for kern in ("default", "v2", "hybrid"):
         if kern == "default":
             os.environ.pop("PYLDA_KERNEL", None)
         else:
             os.environ["PYLDA_KERNEL"] = kern
-        out = ctx.estep(0, eta, alpha, 12, 1e-6, heldout=True, want_alpha_ss=True)
-        print("K=%d" % K, kern, out["doc_ll"], out["stats"]["n_estep_launches"], flush=True)
+        out = ctx.estep(0, eta, alpha, 30, 1e-6, heldout=True, want_alpha_ss=True)
+        st = out["stats"]
+        print("K=%d" % K, kern, out["doc_ll"], st["n_estep_launches"], "narrow", st["docs_narrow_wide"], st["docs_narrow"], flush=True)
+    os.environ.pop("PYLDA_KERNEL", None)
+    ctx.estep_resident(0, 30, 1e-6, want_alpha_ss=True)          # resident EM iteration: device M-step, top words
+    ctx.mstep_resident(1.0 / V, want_eta=False)
+    ctx.top_words(5)
 ctx.close()
 PY
 for tool in memcheck racecheck; do

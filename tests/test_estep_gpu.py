@@ -228,9 +228,10 @@ def test_resident_em_loop_matches_oracle(ctx):
         eta = eta_new
 
 
-def test_page_locked_gamma_buffer_is_written_in_place(ctx):
-    """pylda_estep with a page-locked gamma buffer: the kernels store gamma straight into host memory
-    (no D x K copy at the end); results must be identical to the pageable path."""
+def test_page_locked_gamma_buffer(ctx, monkeypatch):
+    """pylda_estep with a page-locked gamma buffer.  Without the hand-over to the narrow stages the kernels store
+    gamma straight into host memory (no D x K copy at the end); with it (default) gamma leaves by one DMA copy.
+    Either way the results are identical to the pageable path."""
     g = load_golden("zipf48_k100")
     ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
     plain = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6)
@@ -239,13 +240,19 @@ def test_page_locked_gamma_buffer_is_written_in_place(ctx):
     ctx.pin(pinned)
     try:
         out = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned)
-        assert out["gamma"] is pinned
+        assert out["gamma"] is pinned and out["stats"]["docs_narrow"] > 0
         assert numpy.array_equal(pinned, plain["gamma"])
+        assert numpy.array_equal(ctx.get_results(0, gamma=True, phi=False)["gamma"], plain["gamma"])   # still on the device
+        monkeypatch.setenv("PYLDA_PARK", "0")
+        pinned.fill(-1.0)
+        out = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned)
+        assert out["gamma"] is pinned and out["stats"]["docs_narrow"] == 0
+        assert max_rel(pinned, plain["gamma"]) <= 1e-11
         assert out["doc_ll"] == plain["doc_ll"] or abs(out["doc_ll"] - plain["doc_ll"]) <= 1e-12 * abs(plain["doc_ll"])
         with pytest.raises(RuntimeError):
-            ctx.get_results(0, gamma=True, phi=False)        # gamma of that call is not on the device
+            ctx.get_results(0, gamma=True, phi=False)        # gamma of that call was written in place, not on the device
         again = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned, want_alpha_ss=True)   # falls back to the copy
-        assert numpy.array_equal(again["gamma"], plain["gamma"])
+        assert max_rel(again["gamma"], plain["gamma"]) <= 1e-11
     finally:
         ctx.unpin(pinned)
 
