@@ -478,7 +478,8 @@ def run_product(args, cfg):
         e2e = {"value": docs_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": eta_pin.nbytes + alpha.nbytes,
                "d2h_bytes_per_step": gamma_pin.nbytes + phi_pin.nbytes + 64, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "elbo_doc_ll": out["doc_ll"],
-               "host_buffers": "page-locked (cudaHostRegister): eta H2D, gamma and phi_ss D2H by cudaMemcpyAsync"}
+               "host_buffers": "page-locked (cudaHostRegister): eta H2D and phi_ss D2H by cudaMemcpyAsync; the gamma D2H starts "
+                               "when the short documents are final and overlaps the long-document kernels"}
         for a in (eta_pin, gamma_pin, phi_pin):
             ctx.unpin(a)
         del gamma_pin, phi_pin

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 8
+#define PYLDA_ABI_VERSION 9
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -62,6 +62,8 @@ typedef struct pylda_stats {
     int64_t docs_narrow;       /* documents that went through the 8-column narrow stage (at most 8 alive)      */
     double  allreduce_ms;      /* NCCL all-reduce of the V x K statistics, ELBO scalars and alpha statistics
                                   (CUDA-event time on our stream; part of post_ms; 0 on a single rank)          */
+    int64_t gamma_rows_early;  /* rows of gamma whose copy to a page-locked caller buffer (pylda_estep) started before
+                                  the long-document kernels and overlapped them; 0 = gamma left at the end       */
 } pylda_stats;
 
 /* ABI version of the loaded library (== PYLDA_ABI_VERSION of the header it was built from). */
@@ -153,9 +155,11 @@ int pylda_comm_allreduce_sum(pylda_ctx* ctx, double* buf, int64_t n);
 
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister, mapped) so that the H2D/D2H copies of
  * pylda_estep run at full PCIe rate.  Optional: pageable buffers work, only slower.  When the gamma_DxK
- * argument of pylda_estep is page-locked, alpha_ss_K is NULL and the hand-over to the narrow stages is off
- * (alpha too large for topics to die, or PYLDA_PARK=0) the kernels store gamma directly into it over PCIe while
- * they run, instead of a D x K copy at the end of the call. */
+ * argument of pylda_estep is page-locked, the D x K copy of gamma does not wait for the end of the call: the
+ * kernels of the long documents run last and the copy of everything else crosses PCIe beside them (the long
+ * documents' rows follow through the buffer's device alias; pylda_stats.gamma_rows_early).  When the hand-over
+ * to the narrow stages is off (alpha too large for topics to die, or PYLDA_PARK=0) and alpha_ss_K is NULL, the
+ * kernels store gamma directly into the buffer instead. */
 int pylda_host_register(pylda_ctx* ctx, void* ptr, int64_t bytes);
 int pylda_host_unregister(pylda_ctx* ctx, void* ptr);
 

@@ -91,6 +91,11 @@ struct Corpus {
     double* gamma_dst = nullptr;     // where the kernels of the current E-step write gamma: `gamma`, or the
                                      // device alias of a caller's page-locked host buffer (zero-copy D2H)
     bool gamma_on_device = false;
+    // early copy of gamma (estep_resident_impl): the caller's page-locked buffer and its device alias for the
+    // E-step in flight; early_done = the buffer holds the complete gamma when the per-document kernels have finished
+    double* early_host = nullptr;
+    double* early_alias = nullptr;
+    bool early_done = false;
     double* docterm = nullptr;
     int* iters = nullptr;
     bool has_results = false;
@@ -107,7 +112,9 @@ struct pylda_ctx {
     int device = 0;
     cudaDeviceProp prop;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // the early D2H copy of gamma runs beside the long-document kernels
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     std::string err;
     Corpus corp[2];
     // model
@@ -521,6 +528,12 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 16 + li;
         p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
         p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
+        {
+            // which stages hand over (bit 0: 32 -> 16 columns, bit 1: 16 -> 8)
+            const char* h = getenv("PYLDA_NARROW_HANDOVER");
+            const int mask = h ? atoi(h) : 3;
+            p.handover = (NC == 32) ? (mask & 1) : (NC == 16) ? ((mask >> 1) & 1) : 0;
+        }
         void* args[] = {&p};
         timer.begin(ctx->stream, "narrow<%d,%d,%d> smem=%d grid=%lld", NC, G, RPLs[li], smem, grid);
         CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(128), args, (size_t)smem, ctx->stream));
@@ -699,21 +712,23 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     }
     st->docs_streamed = nstream;
     st->docs_resident = D - nstream;
-    if (nstream > 0) {
+    auto launch_long = [&]() -> int {
         // Long documents: the streaming kernel.  (Tried in round 2 and dropped, both measured slower at the headline
         // config -- DESIGN.md section 6: a cluster kernel with the whole tile on chip [estep_hy, kept opt-in], and a
         // 16-warp streaming kernel with a resident shared-memory prefix: streaming is bound by the bytes it keeps in
         // flight towards L2, and one document per SM keeps fewer in flight than two.)
+        if (nstream <= 0) return 0;
         int launched = 0;
         timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream, ns[0]);
         if (launch_stream2(ctx, cp, 0, nstream, ns[0], LK, J, max_iter, tol, st, 17, &launched, pc.nc)) return 1;
         timer.end(ctx->stream);
         if (!launched) return fail(ctx, "no streaming kernel instantiation for LK=%d J=%d", LK, J);
-    }
-    for (int ci = 0; ci < NC; ++ci) {
+        return 0;
+    };
+    auto launch_class = [&](int ci) -> int {
         const Cls& c = cls[ci];
         const long long nd = c.hi - c.lo;
-        if (nd <= 0) continue;
+        if (nd <= 0) return 0;
         const int W = c.W;
         const int kpad = 2 * c.LK * c.J, ln = 32 / c.LK;
         int nmax, G;
@@ -764,8 +779,43 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         timer.end(ctx->stream);
         st->n_launches++;
         st->n_estep_launches++;
-    }
+        return 0;
+    };
+    // Order of the launches.  Kernels that hand documents over to the narrow stages run first, then the narrow
+    // stages, and the kernels that never hand over (the shared-memory classes and, when all its documents are longer
+    // than 192 terms, the streaming kernel) run LAST: at that point gamma is final for every other document, so when
+    // the caller's gamma buffer is page-locked its D x K copy back to the host starts here, on a second stream, and
+    // crosses PCIe beside the long-document kernels instead of after them (800 MB = 15 ms at the headline config).
+    // The rows of the late documents follow through the buffer's device alias (k_copy_rows).
+    const bool stream_parks = nstream > 0 && pc.nc > 0 && ns[(size_t)nstream - 1] <= 192;
+    int nlate = 0;                                          // leading classes that never hand over
+    while (nlate < NC && cls[nlate].kind == 0) ++nlate;
+    const long long late_lo = stream_parks ? nstream : 0;
+    const long long late_hi = nlate ? cls[nlate - 1].hi : nlong;
+    if (stream_parks && launch_long()) return 1;
+    for (int ci = nlate; ci < NC; ++ci)
+        if (launch_class(ci)) return 1;
     if (pc.nc > 0 && launch_narrow(ctx, cp, pc, max_iter, tol, st, timer)) return 1;
+    const bool early = cp.early_host && cp.early_alias && cp.gamma_dst == cp.gamma && late_hi > late_lo && !timer.on;
+    if (early) {
+        CK(cudaEventRecord(ctx->ev_copy[0], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
+        CK(cudaMemcpyAsync(cp.early_host, cp.gamma, (size_t)D * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+    }
+    if (!stream_parks && launch_long()) return 1;
+    for (int ci = 0; ci < nlate; ++ci)
+        if (launch_class(ci)) return 1;
+    if (early) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+        const long long n = late_hi - late_lo;
+        const int blocks = (int)std::min<long long>((n + 7) / 8, (long long)ctx->prop.multiProcessorCount * 8);
+        k_copy_rows<<<blocks, 256, 0, ctx->stream>>>(cp.order + late_lo, n, K, cp.gamma, cp.early_alias);
+        CK(cudaGetLastError());
+        st->n_launches++;
+        st->gamma_rows_early = D - n;
+        cp.early_done = true;
+    }
     timer.report(ctx->stream);
     return 0;
 }
@@ -820,6 +870,8 @@ int pylda_create(pylda_ctx** out, int device) {
         return 1;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (auto& ev : ctx->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaMalloc((void**)&ctx->scal, 8 * sizeof(double));
     cudaMemset(ctx->scal, 0, 8 * sizeof(double));
     cudaMalloc((void**)&ctx->counters, 32 * sizeof(int));
@@ -834,12 +886,15 @@ int pylda_destroy(pylda_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_corpus(ctx->corp[0]);
     free_corpus(ctx->corp[1]);
     free_model(ctx);
     cudaFree(ctx->scal); cudaFree(ctx->partial); cudaFree(ctx->counters); cudaFree(ctx->park_ctr);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -974,17 +1029,18 @@ int pylda_set_alpha(pylda_ctx* ctx, const double* alpha_K) {
 }
 
 static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
-                               pylda_stats* stats, double* gamma_host_alias);
+                               pylda_stats* stats, double* gamma_host_alias, double* gamma_host);
 
 int pylda_estep_resident(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
                          pylda_stats* stats) {
-    return estep_resident_impl(ctx, slot, max_iter, tol, heldout, want_alpha_ss, stats, nullptr);
+    return estep_resident_impl(ctx, slot, max_iter, tol, heldout, want_alpha_ss, stats, nullptr, nullptr);
 }
 
-// gamma_host_alias: device-visible alias of a page-locked caller buffer; when given, the per-document
-// kernels store gamma straight into it (the D x K copy back disappears from the end of the call)
+// gamma_host / gamma_host_alias: a page-locked caller buffer and its device-visible alias; when given, gamma reaches
+// it without a D x K copy at the end of the call -- the kernels store straight into it (no narrow stages), or the
+// copy starts as soon as the short documents are final and overlaps the long-document kernels (launch_estep)
 static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double tol, int heldout, int want_alpha_ss,
-                               pylda_stats* stats, double* gamma_host_alias) {
+                               pylda_stats* stats, double* gamma_host_alias, double* gamma_host) {
     if (!ctx) return 1;
     if (slot < 0 || slot > 1) return fail(ctx, "pylda_estep: slot must be 0 or 1");
     if (!ctx->model_set) return fail(ctx, "pylda_estep: no model on the device (pylda_set_model)");
@@ -1004,6 +1060,13 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
     const bool zero_copy = gamma_host_alias && !want_alpha_ss && park_config(ctx).nc == 0;
     cp.gamma_dst = zero_copy ? gamma_host_alias : cp.gamma;
     cp.gamma_on_device = (cp.gamma_dst == cp.gamma);
+    {
+        const char* ec = getenv("PYLDA_EARLY_COPY");
+        const bool on = gamma_host_alias && gamma_host && !zero_copy && !(ec && !strcmp(ec, "0"));
+        cp.early_host = on ? gamma_host : nullptr;
+        cp.early_alias = on ? gamma_host_alias : nullptr;
+        cp.early_done = false;
+    }
     const int nred = ctx->prop.multiProcessorCount * 2;
     const int nass = ctx->prop.multiProcessorCount * 2;
     if (ensure_partial(ctx, std::max((size_t)nred * NTERMS, std::max((size_t)nass * K, (size_t)2 * 64 * K)))) return 1;
@@ -1099,7 +1162,7 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
         // the counter is local, so the ranks agree on it first).
         const int64_t seen = st.revived_docs;
         ctx->force_full = true;
-        const int rc = estep_resident_impl(ctx, slot, max_iter, tol, heldout, want_alpha_ss, &st, gamma_host_alias);
+        const int rc = estep_resident_impl(ctx, slot, max_iter, tol, heldout, want_alpha_ss, &st, gamma_host_alias, gamma_host);
         ctx->force_full = false;
         if (rc) return 1;
         st.revived_docs = seen;
@@ -1149,17 +1212,17 @@ int pylda_estep(pylda_ctx* ctx, int slot, int K, int V, const double* eta_KxV, c
                 double* words_ll, pylda_stats* stats) {
     if (!ctx) return 1;
     if (pylda_set_model(ctx, K, V, eta_KxV, alpha_K)) return 1;
-    // page-locked (pylda_host_register / cudaHostAlloc) gamma buffer: let the kernels write into it
+    // page-locked (pylda_host_register / cudaHostAlloc) gamma buffer: the kernels write into it, or its copy starts early
     double* alias = nullptr;
-    if (gamma_DxK && !alpha_ss_K) {
+    if (gamma_DxK) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, gamma_DxK) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             alias = (double*)at.devicePointer;
         else
             cudaGetLastError();
     }
-    if (estep_resident_impl(ctx, slot, max_iter, tol, heldout, alpha_ss_K != nullptr, stats, alias)) return 1;
-    const bool direct = alias && !ctx->corp[slot].gamma_on_device;
+    if (estep_resident_impl(ctx, slot, max_iter, tol, heldout, alpha_ss_K != nullptr, stats, alias, gamma_DxK)) return 1;
+    const bool direct = alias && (!ctx->corp[slot].gamma_on_device || ctx->corp[slot].early_done);
     return pylda_get_results(ctx, slot, direct ? nullptr : gamma_DxK, phi_ss_KxV, alpha_ss_K, doc_ll, words_ll, nullptr);
 }
 

@@ -64,6 +64,7 @@ struct NParams {
     int* lists;                          // all PARK_LISTS lists (hand-over 16 -> 8 columns)
     int* counts;
     int cap;                             // capacity of one list
+    int handover;                        // hand a document over to the next narrower stage at NC / 2 live topics
     double chk_bound;                    // sum_n w_n <= chk_bound proves that no eliminated topic can come back
     int* revived;                        // counter of documents in which one would have
 };
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(128, MINB) estep_narrow(const NParams p) {
                     bal[u] = __ballot_sync(0xffffffffu, lv[u]) & gmask;
                     nl += __popc(bal[u]);
                 }
-                if (running && !fin && nl <= NC / 2) {
+                if (p.handover && running && !fin && nl <= NC / 2) {
                     int* wrec = p.rec + (size_t)d * PARK_REC;
                     const unsigned below = gmask & ((1u << lane) - 1u);
                     int rank = 0;

@@ -307,4 +307,17 @@ __global__ void k_dead_phi(const double* __restrict__ Bt, const double* __restri
     }
 }
 
+// gamma rows of the documents order[0 .. n) from the device array into the device alias of the caller's page-locked
+// buffer (one warp per document, 256-byte stores): the rows that were not final yet when the early copy of gamma
+// started (capi.cu, estep_resident_impl)
+__global__ void k_copy_rows(const int* __restrict__ order, long long n, int K, const double* __restrict__ src,
+                            double* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const size_t o = (size_t)order[i] * K;
+        for (int k = lane; k < K; k += 32) dst[o + k] = src[o + k];
+    }
+}
+
 }  // namespace pylda

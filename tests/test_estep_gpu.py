@@ -230,19 +230,31 @@ def test_resident_em_loop_matches_oracle(ctx):
 
 def test_page_locked_gamma_buffer(ctx, monkeypatch):
     """pylda_estep with a page-locked gamma buffer.  Without the hand-over to the narrow stages the kernels store
-    gamma straight into host memory (no D x K copy at the end); with it (default) gamma leaves by one DMA copy.
-    Either way the results are identical to the pageable path."""
+    gamma straight into host memory (no D x K copy at the end); with it (default) gamma leaves by DMA, and the copy
+    starts before the kernels of the long documents (which run last), whose rows follow through the buffer's device
+    alias.  Either way the results are identical to the pageable path."""
     g = load_golden("zipf48_k100")
     ctx.set_corpus(0, g["row_ptr"], g["ids"], g["cts"])
     plain = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6)
     D = len(g["row_ptr"]) - 1
+    n_late = int((numpy.diff(g["row_ptr"]) > 272).sum())     # longer than every register / shared-memory class at K = 100
+    assert 0 < n_late < D
     pinned = numpy.full((D, g["K"]), -1.0)
     ctx.pin(pinned)
     try:
         out = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned)
         assert out["gamma"] is pinned and out["stats"]["docs_narrow"] > 0
+        assert 0 < out["stats"]["gamma_rows_early"] <= D - n_late
         assert numpy.array_equal(pinned, plain["gamma"])
         assert numpy.array_equal(ctx.get_results(0, gamma=True, phi=False)["gamma"], plain["gamma"])   # still on the device
+        pinned.fill(-1.0)
+        both = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned, want_alpha_ss=True)
+        assert both["stats"]["gamma_rows_early"] > 0 and numpy.array_equal(pinned, plain["gamma"])
+        monkeypatch.setenv("PYLDA_EARLY_COPY", "0")
+        pinned.fill(-1.0)
+        late = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned)
+        assert late["stats"]["gamma_rows_early"] == 0 and numpy.array_equal(pinned, plain["gamma"])
+        monkeypatch.delenv("PYLDA_EARLY_COPY")
         monkeypatch.setenv("PYLDA_PARK", "0")
         pinned.fill(-1.0)
         out = ctx.estep(0, g["eta"], g["alpha"], 50, 1e-6, gamma_out=pinned)
