@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Benchmark of the VB E-step (variational_bayes.py:132-216) on BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c3|c5|c5x]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c5|c5x]
                     [--scaling weak|strong] [--docs D] [--state cold|warm]
 
 Workloads (`--config`):
+  c2   configs[1]: synthetic D = 100k docs, V = 10k, K = 50, ~100 tokens per document
   c3   BASELINE.json configs[2], the headline: synthetic D = 1M docs, V = 100k, K = 100, Zipf document lengths
   c5   configs[4]: D = 1.25M docs per GPU, V = 1M, K = 500, ~100 tokens per document
   c5x  configs[4] contention stress: the same with word exponent 1.3 (hot words hit by most documents)
@@ -45,6 +46,9 @@ METRIC_C3 = "E-step docs/sec at K=100, V=100k (synthetic Zipf-length corpus)"
 UNIT = "docs/s"
 
 CONFIGS = {
+    "c2": dict(K=50, V=10000, D=100000, length="poisson", mean_len=100, word_exponent=1.0, seed=1235,
+               metric="E-step docs/sec at K=50, V=10k (synthetic ~100-token documents)",
+               label="configs[1]: synthetic D=%(D)d docs%(per)s, V=%(V)d, K=%(K)d, ~100 tokens per document (nnz=%(nnz)d on rank 0)"),
     "c3": dict(K=100, V=100000, D=1000000, length="zipf", mean_len=100, word_exponent=1.0, seed=1236, metric=METRIC_C3,
                label="configs[2]: synthetic D=%(D)d docs%(per)s, V=%(V)d, K=%(K)d, Zipf lengths (nnz=%(nnz)d on rank 0)"),
     "c5": dict(K=500, V=1000000, D=1250000, length="poisson", mean_len=100, word_exponent=1.0, seed=1238,
@@ -385,23 +389,29 @@ def run_product(args, cfg):
 
     em_stats = {}
 
-    def warm_model(want_eta, n_docs_total):
+    em_state = {}
+
+    def warm_model(want_eta, n_docs_total, n_em=4, restart=True):
         """EM iterations 1..4 of variational_bayes.py:239-261 with everything resident: device E-step, device
         M-step, alpha statistics from the device (summed over ranks by the library) and the reference's Newton
-        update of alpha on the host (K numbers).  Leaves the model of EM iteration 5 on the device."""
+        update of alpha on the host (K numbers).  Leaves the model of EM iteration 5 on the device.
+        restart=False: n_em further iterations on the model and alpha the previous call left."""
         from pylda_b200.variational_bayes import VariationalBayes
-        shell = VariationalBayes()
-        shell._number_of_topics = K
-        shell._number_of_documents = int(n_docs_total)
-        shell._alpha_alpha = alpha.copy()
-        ctx.set_model(eta0, alpha)
+        if restart:
+            shell = VariationalBayes()
+            shell._number_of_topics = K
+            shell._number_of_documents = int(n_docs_total)
+            shell._alpha_alpha = alpha.copy()
+            ctx.set_model(eta0, alpha)
+            em_state["shell"] = shell
+        shell = em_state["shell"]
         eta_host = None
         em_wall = []
-        for em in range(4):
+        for em in range(n_em):
             t_em = time.perf_counter()
             ctx.estep_resident(0, 50, 1e-6, want_alpha_ss=True)
             alpha_ss = ctx.get_results(0, gamma=False, phi=False, alpha_ss=True)["alpha_ss"]
-            _, eta_host = ctx.mstep_resident(alpha_beta, want_eta=(want_eta and em == 3))
+            _, eta_host = ctx.mstep_resident(alpha_beta, want_eta=(want_eta and em == n_em - 1))
             shell.optimize_hyperparameters(alpha_ss)
             ctx.set_alpha(shell._alpha_alpha)
             em_wall.append(time.perf_counter() - t_em)
@@ -518,6 +528,15 @@ def run_product(args, cfg):
                     "mean_inner_trips": lst["inner_iters"] / lda_total,
                     "roofline_frac": lst["algo_total_bytes"] / (lk * 1e-3) / 1e9 / peak,
                     "roofline_frac_read": lst["algo_read_bytes"] / (lk * 1e-3) / 1e9 / peak}
+        # ... and later in the same training run (EM iteration 20), where fewer trips are left per document
+        warm_model(False, lda_total, n_em=15, restart=False)
+        for _ in range(2):
+            ctx.estep_resident(0, 50, 1e-6)
+        _, ldev, lker, lst = timed_resident(3)
+        lms, lk = allmax(sum(ldev) / 3), allmax(sum(lker) / 3)
+        warm_lda["em_iteration_20"] = {"value": lda_total / (lms * 1e-3), "unit": UNIT, "ms_per_step": lms, "kernel_ms": lk,
+                                       "mean_inner_trips": lst["inner_iters"] / lda_total,
+                                       "roofline_frac": lst["algo_total_bytes"] / (lk * 1e-3) / 1e9 / peak}
 
     if rank == 0:
         traffic, traffic_note = measured_traffic(args.config, args.docs)
@@ -633,7 +652,7 @@ def main():
     cfg = CONFIGS[args.config]
     if args.docs is None:
         args.docs = cfg["D"]
-    if args.config != "c3":                      # the K = 500 configs: 4 GB tables; keep the run bounded
+    if args.config not in ("c2", "c3"):          # the K = 500 configs: 4 GB tables; keep the run bounded
         args.no_warm = True
         args.no_warm_lda = True
     if args.warmup < 3 and args.impl == "b200":

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PYLDA_ABI_VERSION 9
+#define PYLDA_ABI_VERSION 10
 #define PYLDA_NCCL_ID_BYTES 128
 
 typedef struct pylda_ctx pylda_ctx;
@@ -64,6 +64,8 @@ typedef struct pylda_stats {
                                   (CUDA-event time on our stream; part of post_ms; 0 on a single rank)          */
     int64_t gamma_rows_early;  /* rows of gamma whose copy to a page-locked caller buffer (pylda_estep) started before
                                   the long-document kernels and overlapped them; 0 = gamma left at the end       */
+    int64_t docs_long_compact; /* documents of more than 192 terms finished by the compact stage for long documents
+                                  (at most 32 topics alive)                                                      */
 } pylda_stats;
 
 /* ABI version of the loaded library (== PYLDA_ABI_VERSION of the header it was built from). */

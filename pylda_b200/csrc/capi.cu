@@ -17,6 +17,7 @@
 #include "estep_dispatch.h"
 #include "estep_kernel.cuh"
 #include "estep_narrow.cuh"
+#include "estep_longc.cuh"
 #include "estep_sweep.cuh"
 #include "prep_kernels.cuh"
 
@@ -112,6 +113,14 @@ struct pylda_ctx {
     int device = 0;
     cudaDeviceProp prop;
     cudaStream_t stream = nullptr;
+    double* flat_part = nullptr;             // k_build_B: per-block sums of Bt; flat_dev / flat_host: their total
+    double* flat_dev = nullptr;
+    double* flat_host = nullptr;             // page-locked
+    cudaEvent_t ev_flat = nullptr;
+    double* longc_tile = nullptr;            // scratch of estep_longc (per CTA: compact tile, counts, term ids)
+    double* longc_cnt = nullptr;
+    int* longc_ids = nullptr;
+    size_t longc_rows = 0;
     cudaStream_t copy_stream = nullptr;      // the early D2H copy of gamma runs beside the long-document kernels
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
@@ -341,8 +350,11 @@ int prepare_tables(pylda_ctx* ctx, bool heldout, int* launches) {
     dim3 tb(32, 8), tg((V + 31) / 32, (K + 31) / 32);
     k_elog_transpose<<<tg, tb, 0, ctx->stream>>>(ctx->eta, psisum, K, V, KP, ctx->Elt);
     const int nb = std::min((V + 7) / 8, ctx->prop.multiProcessorCount * 8);
-    k_build_B<<<nb, 256, 0, ctx->stream>>>(ctx->Elt, K, V, KP, ctx->Bt, ctx->mw, ctx->phi);
-    *launches += 4;
+    k_build_B<<<nb, 256, 0, ctx->stream>>>(ctx->Elt, K, V, KP, ctx->Bt, ctx->mw, ctx->phi, ctx->flat_part);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->flat_part, nb, 1, ctx->flat_dev);
+    CK(cudaMemcpyAsync(ctx->flat_host, ctx->flat_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_flat, ctx->stream));
+    *launches += 5;
     if (heldout) {
         const int nchunk = 64;
         if (ensure_partial(ctx, (size_t)2 * nchunk * K)) return 1;
@@ -413,7 +425,7 @@ struct ClassTimer {
 
 // second-generation streaming kernel for documents [lo, hi) of the sorted order (all with n <= nmax)
 int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int nmax, int LK, int J, int max_iter,
-                   double tol, pylda_stats* st, int counter_slot, int* launched, int park_nc) {
+                   double tol, pylda_stats* st, int counter_slot, int* launched, int park_nc, int park_long) {
     *launched = 0;
     const int K = ctx->K, KP = ctx->KP;
     const int KPAD = 2 * LK * J, LN = 32 / LK, W = 8;
@@ -425,8 +437,8 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
     const int cap = std::min((nmax + W * LN - 1) / (W * LN) * (W * LN), limit);
     // lean instantiation when no document of the class can be handed over (all longer than 192 terms) or chunked
     const int nmin = cp.n_sorted[(size_t)hi - 1];
-    const bool full = (park_nc > 0 && nmin <= 192) || nmax > cap;
-    const void* fn = estep_stream_lookup(LK, J, full);
+    const bool parks = (park_nc > 0 && nmin <= 192) || (park_long > 192 && nmin <= park_long);
+    const void* fn = estep_stream_lookup(LK, J, nmax > cap ? 1 : parks ? 2 : 0);
     if (!fn) return 0;
     GroupLayout gl;
     int o = 16 + KPAD * 8;
@@ -453,7 +465,7 @@ int launch_stream2(pylda_ctx* ctx, Corpus& cp, long long lo, long long hi, int n
         const char* z = getenv("PYLDA_ZIGZAG");                 // alternate the row order trip by trip (L1 reuse)
         p.compact = !(z && !strcmp(z, "0"));
     }
-    p.park_nc = park_nc;
+    p.park_nc = park_nc; p.park_long = park_long;
     p.park_rec = cp.park_rec; p.park_gam = cp.park_gam; p.park_lists = cp.park_lists;
     p.park_counts = ctx->park_ctr; p.park_cap = (int)cp.D;
     p.off_spart = gl.off_spart; p.off_red = gl.off_red; p.off_cnt = gl.off_cnt; p.off_rid = gl.off_rid;
@@ -477,7 +489,7 @@ double host_digamma(double x) {
 // e_k s_k < ulp(alpha_k)/2, s_k <= sum_n w_n; chk_bound = alpha_min 2^-54 / exp(psi(alpha_max)) is the value
 // of sum_n w_n below which that is certain.  The hand-over is only used when the bound leaves three orders
 // of magnitude of room (alpha <~ 0.02); the kernels check every document against it.
-struct ParkCfg { int nc; double chk_bound; };
+struct ParkCfg { int nc; double chk_bound; int long_rows; };   // long_rows: longest document estep_longc takes (0: off)
 ParkCfg park_config(const pylda_ctx* ctx) {
     ParkCfg c;
     const char* e = getenv("PYLDA_PARK");
@@ -489,19 +501,95 @@ ParkCfg park_config(const pylda_ctx* ctx) {
     if (!(c.chk_bound >= 1e3)) c.nc = 0;
     const char* ce = getenv("PYLDA_COMPACT");
     if ((ce && !strcmp(ce, "0")) || ctx->force_full) c.nc = 0;
+    // Long documents (> 192 terms) are handed to estep_longc at <= 32 live topics; its per-CTA scratch is sized for
+    // the longest document it may get, hence the cap.
+    c.long_rows = (c.nc >= 16) ? 16384 : 0;
+    if (const char* pl = getenv("PYLDA_PARK_LONG")) c.long_rows = (c.nc >= 16) ? std::max(0, atoi(pl)) : 0;
     return c;
 }
 
-int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, double tol, pylda_stats* st, ClassTimer& timer) {
+// parameters common to the narrow stages and estep_longc, for park list li
+NParams narrow_params(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int li, int max_iter, double tol) {
+    NParams p;
+    memset(&p, 0, sizeof p);
+    p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
+    p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.e_dead = ctx->e_dead;
+    p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.wsum = ctx->wsum; p.docterm = cp.docterm; p.iters = cp.iters;
+    p.K = ctx->K; p.KP = ctx->KP; p.max_iter = max_iter; p.tol = tol;
+    p.lg_alpha = ctx->lg_alpha; p.alpha_sum = ctx->alpha_sum;
+    p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 16 + li;
+    p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
+    p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
+    return p;
+}
+
+// before the first kernel that adds to wsum
+int narrow_begin(pylda_ctx* ctx, pylda_stats* st) {
     k_e_dead<<<(ctx->K + 127) / 128, 128, 0, ctx->stream>>>(ctx->alpha, ctx->K, ctx->e_dead);
     CK(cudaMemsetAsync(ctx->wsum, 0, (size_t)ctx->V * sizeof(double), ctx->stream));
     st->n_launches++;
+    return 0;
+}
+
+// after the last one: the statistics of the eliminated topics, for every document that finished in a compact stage
+int narrow_end(pylda_ctx* ctx, pylda_stats* st, ClassTimer& timer) {
+    timer.begin(ctx->stream, "dead-topic statistics (k_dead_phi)");
+    k_dead_phi<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->Bt, ctx->wsum, ctx->e_dead, ctx->K, ctx->V,
+                                                                         ctx->KP, ctx->phi);
+    timer.end(ctx->stream);
+    CK(cudaGetLastError());
+    st->n_launches++;
+    return 0;
+}
+
+// Compact stage for long documents (estep_longc.cuh): park list 9, fed by estep_stream and estep_v2.
+int launch_longc(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int nmax, long long ndocs_max, int max_iter, double tol,
+                 pylda_stats* st, ClassTimer& timer) {
+    const void* fn = estep_longc_lookup(32);
+    if (!fn) return fail(ctx, "no compact-stage kernel for long documents");
+    const int NC = 32, K = ctx->K;
+    const int fixed = (NC + 8 * NC + 4 * 8 + 2 + ((K + 1) & ~1)) * (int)sizeof(double);
+    // shared-memory tile: documents of up to smem_rows rows never leave the SM; two CTAs per SM
+    int budget = 96 * 1024;
+    if (const char* e = getenv("PYLDA_LONGC_SMEM")) budget = std::max(0, atoi(e)) * 1024;
+    int smem_rows = std::max(0, (budget - fixed) / (NC * 8)) / 64 * 64;
+    const int scratch_rows = std::min((nmax + 63) / 64 * 64, (pc.long_rows + 63) / 64 * 64);
+    smem_rows = std::min(smem_rows, scratch_rows);
+    const int smem = fixed + smem_rows * NC * 8;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, smem, 0));
+    if (occ < 1) return fail(ctx, "internal: zero occupancy for the long-document compact stage (smem %d)", smem);
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)ctx->prop.multiProcessorCount * occ, ndocs_max));
+    const size_t need = (size_t)grid * scratch_rows;
+    if (ctx->longc_rows < need) {
+        if (ctx->longc_tile) { cudaFree(ctx->longc_tile); cudaFree(ctx->longc_cnt); cudaFree(ctx->longc_ids); }
+        ctx->longc_tile = nullptr; ctx->longc_cnt = nullptr; ctx->longc_ids = nullptr; ctx->longc_rows = 0;
+        CK(dalloc(&ctx->longc_tile, need * NC));
+        CK(dalloc(&ctx->longc_cnt, need));
+        CK(dalloc(&ctx->longc_ids, need));
+        ctx->longc_rows = need;
+    }
+    LParams lp;
+    lp.n = narrow_params(ctx, cp, pc, 9, max_iter, tol);
+    lp.scratch_tile = ctx->longc_tile; lp.scratch_cnt = ctx->longc_cnt; lp.scratch_ids = ctx->longc_ids;
+    lp.scratch_rows = scratch_rows; lp.smem_rows = smem_rows;
+    void* args[] = {&lp};
+    timer.begin(ctx->stream, "longc<%d> smem=%d (tile rows %d) scratch rows %d grid=%lld", NC, smem, smem_rows, scratch_rows, grid);
+    CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)smem, ctx->stream));
+    timer.end(ctx->stream);
+    st->n_launches++;
+    st->n_estep_launches++;
+    return 0;
+}
+
+int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, double tol, pylda_stats* st, ClassTimer& timer) {
     // launch order: the 32-column list (8) feeds the 16-column ones (0, 1, 2, 7), which feed the 8-column ones (3..6)
-    static const int order[PARK_LISTS] = {8, 0, 1, 2, 7, 3, 4, 5, 6};
-    static const int NCs[PARK_LISTS] = {16, 16, 16, 8, 8, 8, 8, 16, 32};
-    static const int Gs[PARK_LISTS] = {8, 16, 32, 4, 8, 16, 32, 32, 32};
-    static const int RPLs[PARK_LISTS] = {3, 3, 3, 6, 6, 6, 6, 6, 3};
-    for (int oi = 0; oi < PARK_LISTS; ++oi) {
+    static const int order[PARK_NARROW_LISTS] = {8, 0, 1, 2, 7, 3, 4, 5, 6};
+    static const int NCs[PARK_NARROW_LISTS] = {16, 16, 16, 8, 8, 8, 8, 16, 32};
+    static const int Gs[PARK_NARROW_LISTS] = {8, 16, 32, 4, 8, 16, 32, 32, 32};
+    static const int RPLs[PARK_NARROW_LISTS] = {3, 3, 3, 6, 6, 6, 6, 6, 3};
+    for (int oi = 0; oi < PARK_NARROW_LISTS; ++oi) {
         const int li = order[oi];
         if (NCs[li] > 8 && pc.nc < 16) continue;        // PYLDA_PARK=8: the 8-column stage only
         const int NC = NCs[li], G = Gs[li];
@@ -518,16 +606,7 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         // the list length is only known on the device: size the grid for the documents that could be there
         long long grid = (long long)ctx->prop.multiProcessorCount * occ;
         grid = std::max<long long>(1, std::min<long long>(grid, (cp.D * G + 127) / 128));
-        NParams p;
-        memset(&p, 0, sizeof p);
-        p.row_ptr = cp.row_ptr; p.ids = cp.ids; p.cts = cp.cts;
-        p.Bt = ctx->Bt; p.mw = ctx->mw; p.alpha = ctx->alpha; p.e_dead = ctx->e_dead;
-        p.gamma = cp.gamma_dst; p.phi_ss = ctx->phi; p.wsum = ctx->wsum; p.docterm = cp.docterm; p.iters = cp.iters;
-        p.K = ctx->K; p.KP = ctx->KP; p.max_iter = max_iter; p.tol = tol;
-        p.lg_alpha = ctx->lg_alpha; p.alpha_sum = ctx->alpha_sum;
-        p.list = cp.park_lists + (size_t)li * cp.D; p.count = ctx->park_ctr + li; p.head = ctx->park_ctr + 16 + li;
-        p.rec = cp.park_rec; p.gam = cp.park_gam; p.lists = cp.park_lists; p.counts = ctx->park_ctr; p.cap = (int)cp.D;
-        p.chk_bound = pc.chk_bound; p.revived = ctx->counters + 14;
+        NParams p = narrow_params(ctx, cp, pc, li, max_iter, tol);
         {
             // which stages hand over (bit 0: 32 -> 16 columns, bit 1: 16 -> 8)
             const char* h = getenv("PYLDA_NARROW_HANDOVER");
@@ -541,12 +620,6 @@ int launch_narrow(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int max_iter, d
         st->n_launches++;
         st->n_estep_launches++;
     }
-    timer.begin(ctx->stream, "dead-topic statistics (k_dead_phi)");
-    k_dead_phi<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->Bt, ctx->wsum, ctx->e_dead, ctx->K, ctx->V,
-                                                                         ctx->KP, ctx->phi);
-    timer.end(ctx->stream);
-    CK(cudaGetLastError());
-    st->n_launches++;
     return 0;
 }
 
@@ -712,6 +785,20 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     }
     st->docs_streamed = nstream;
     st->docs_resident = D - nstream;
+    // Hand-over of LONG documents from the streaming kernel: its parking instantiation costs ~6 % in the trip loop
+    // (register spills), which pays when long documents get down to 32 live topics with many trips left -- any model
+    // after the first M-step (trip ~20 of 50) -- and does not at EM iteration 1, where the random initial topics are
+    // nearly flat and a long document keeps more than 32 topics alive until trip ~45.  The two are told apart by the
+    // model itself: mean_w sum_k B[w,k] / K (B = exp(E[log beta]) scaled to max 1 per word; k_build_B) is ~0.7 for
+    // eta0 ~ Gamma(100, 1/100) and < 0.1 after one M-step.  A deterministic function of eta: the same model always
+    // takes the same path.  Only speed depends on it.
+    int stream_long = pc.long_rows;
+    if (stream_long > 0 && nstream > 0) {
+        CK(cudaEventSynchronize(ctx->ev_flat));
+        double thr = 0.3;
+        if (const char* e = getenv("PYLDA_FLAT_THRESHOLD")) thr = atof(e);
+        if (*ctx->flat_host / ((double)ctx->V * K) > thr) stream_long = 0;
+    }
     auto launch_long = [&]() -> int {
         // Long documents: the streaming kernel.  (Tried in round 2 and dropped, both measured slower at the headline
         // config -- DESIGN.md section 6: a cluster kernel with the whole tile on chip [estep_hy, kept opt-in], and a
@@ -720,7 +807,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
         if (nstream <= 0) return 0;
         int launched = 0;
         timer.begin(ctx->stream, "stream2<%d,%d> docs=%lld nmax=%d", LK, J, nstream, ns[0]);
-        if (launch_stream2(ctx, cp, 0, nstream, ns[0], LK, J, max_iter, tol, st, 17, &launched, pc.nc)) return 1;
+        if (launch_stream2(ctx, cp, 0, nstream, ns[0], LK, J, max_iter, tol, st, 17, &launched, pc.nc, stream_long)) return 1;
         timer.end(ctx->stream);
         if (!launched) return fail(ctx, "no streaming kernel instantiation for LK=%d J=%d", LK, J);
         return 0;
@@ -767,6 +854,7 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
             p.compact = !(ce && !strcmp(ce, "0")) && !ctx->force_full;
             p.revived = ctx->counters + 14;
             p.park_nc = (c.kind == 1) ? pc.nc : 0;
+            p.park_long = (c.kind == 0) ? pc.long_rows : 0;
             p.park_rec = cp.park_rec; p.park_gam = cp.park_gam; p.park_lists = cp.park_lists;
             p.park_counts = ctx->park_ctr; p.park_cap = (int)cp.D;
         }
@@ -787,11 +875,14 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     // the caller's gamma buffer is page-locked its D x K copy back to the host starts here, on a second stream, and
     // crosses PCIe beside the long-document kernels instead of after them (800 MB = 15 ms at the headline config).
     // The rows of the late documents follow through the buffer's device alias (k_copy_rows).
+    // (The late kernels hand their documents to estep_longc, which runs after them; the narrow stages have nothing
+    // to do with documents of more than 192 terms.)
     const bool stream_parks = nstream > 0 && pc.nc > 0 && ns[(size_t)nstream - 1] <= 192;
-    int nlate = 0;                                          // leading classes that never hand over
+    int nlate = 0;                                          // leading classes that never hand over to the narrow stages
     while (nlate < NC && cls[nlate].kind == 0) ++nlate;
     const long long late_lo = stream_parks ? nstream : 0;
     const long long late_hi = nlate ? cls[nlate - 1].hi : nlong;
+    if (pc.nc > 0 && narrow_begin(ctx, st)) return 1;
     if (stream_parks && launch_long()) return 1;
     for (int ci = nlate; ci < NC; ++ci)
         if (launch_class(ci)) return 1;
@@ -806,6 +897,13 @@ int launch_estep(pylda_ctx* ctx, Corpus& cp, int max_iter, double tol, pylda_sta
     if (!stream_parks && launch_long()) return 1;
     for (int ci = 0; ci < nlate; ++ci)
         if (launch_class(ci)) return 1;
+    if (pc.nc > 0) {
+        // documents of more than 192 terms that got down to 32 live topics (from either order of the kernels above)
+        const long long nlong_docs = first_leq(192);
+        if (pc.long_rows > 192 && nlong_docs > 0 &&
+            launch_longc(ctx, cp, pc, ns[0], nlong_docs, max_iter, tol, st, timer)) return 1;
+        if (narrow_end(ctx, st, timer)) return 1;
+    }
     if (early) {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
         const long long n = late_hi - late_lo;
@@ -871,6 +969,10 @@ int pylda_create(pylda_ctx** out, int device) {
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaMalloc((void**)&ctx->flat_part, (size_t)(prop.multiProcessorCount * 8 + 1) * sizeof(double));
+    ctx->flat_dev = ctx->flat_part + (size_t)prop.multiProcessorCount * 8;
+    cudaMallocHost((void**)&ctx->flat_host, sizeof(double));
+    cudaEventCreateWithFlags(&ctx->ev_flat, cudaEventDisableTiming);
     for (auto& ev : ctx->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaMalloc((void**)&ctx->scal, 8 * sizeof(double));
     cudaMemset(ctx->scal, 0, 8 * sizeof(double));
@@ -892,6 +994,9 @@ int pylda_destroy(pylda_ctx* ctx) {
     free_corpus(ctx->corp[1]);
     free_model(ctx);
     cudaFree(ctx->scal); cudaFree(ctx->partial); cudaFree(ctx->counters); cudaFree(ctx->park_ctr);
+    cudaFree(ctx->longc_tile); cudaFree(ctx->longc_cnt); cudaFree(ctx->longc_ids);
+    cudaFree(ctx->flat_part); cudaFreeHost(ctx->flat_host);
+    if (ctx->ev_flat) cudaEventDestroy(ctx->ev_flat);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_copy) if (ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1150,6 +1255,7 @@ static int estep_resident_impl(pylda_ctx* ctx, int slot, int max_iter, double to
         st.revived_docs = rv;
         st.docs_narrow_wide = (long long)pk[0] + pk[1] + pk[2] + pk[7] + pk[8];
         st.docs_narrow = (long long)pk[3] + pk[4] + pk[5] + pk[6];
+        st.docs_long_compact = pk[9];
     }
     st.algo_read_bytes = 8.0 * cp.D + 8.0 * cp.nnz + 8.0 * (double)cp.nnz * K;
     st.algo_total_bytes = st.algo_read_bytes + 8.0 * (double)cp.D * K + 8.0 * (double)cp.nnz * K;

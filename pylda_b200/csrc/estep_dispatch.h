@@ -17,9 +17,12 @@ const void* estep_rt_lk8(int J, int W, int R, int NWARPS, int* rows_per_lane);
 const void* estep_rt_lk16(int J, int W, int R, int NWARPS, int* rows_per_lane);
 const void* estep_rt_lk32(int J, int W, int R, int NWARPS, int* rows_per_lane);
 // second-generation streaming kernel (documents longer than every resident class)
-const void* estep_stream_lookup(int LK, int J, bool full);
+// mode 0: lean, 1: hand-over + chunked staging, 2: hand-over only
+const void* estep_stream_lookup(int LK, int J, int mode);
 // hybrid register / shared-memory tile kernel for long documents (estep_hy.cuh), clusters of 1, 2, 4, 8 CTAs
 const void* estep_hy_lookup(int LK, int J, int* rows_per_lane);
 // narrow stages (estep_narrow.cuh): NC = 16 / 8 live columns, G lanes per document
 const void* estep_narrow_lookup(int NC, int G, int RPL, int MINB);
+// compact stage for long documents (estep_longc.cuh): NC = 32 live columns
+const void* estep_longc_lookup(int NC);
 }  // namespace pylda

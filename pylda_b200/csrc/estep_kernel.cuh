@@ -53,6 +53,7 @@ struct EParams {
     int* revived;                    // estep_rt: counter of documents in which an eliminated topic came back
     // hand-over to the narrow stages (estep_narrow.cuh); park_nc = 0: off, 16 / 8: live-topic threshold
     int park_nc;
+    int park_long;                   // documents of 193 .. park_long terms are handed to estep_longc at <= 32 live topics (0: off)
     int* park_rec;                   // PARK_REC ints per document
     double* park_gam;                // PARK_GAM doubles per document
     int* park_lists;                 // PARK_LISTS lists of park_cap documents

@@ -27,13 +27,17 @@ namespace pylda {
 
 constexpr int PARK_REC = 36;    // ints per parked document: [0] trips done, [1] live topics, [2..34) their columns
 constexpr int PARK_GAM = 32;    // doubles per parked document: gamma of the live topics (same order)
-constexpr int PARK_LISTS = 9;   // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96) [0..2] and G = 32 with 6 rows per lane
+constexpr int PARK_LISTS = 10;  // 16-column stage: G = 8, 16, 32 (n <= 24, 48, 96) [0..2] and G = 32 with 6 rows per lane
                                 // (n <= 192) [7]; 8-column stage: G = 4, 8, 16, 32 (n <= 24, 48, 96, 192) [3..6];
-                                // 32-column stage: G = 32 (n <= 96) [8], fed by the kernels without a compact stage
+                                // 32-column stage: G = 32 (n <= 96) [8], fed by the kernels without a compact stage;
+                                // long documents (n > 192, at most 32 topics alive) [9]: estep_longc.cuh
+constexpr int PARK_NARROW_LISTS = 9;   // lists served by estep_narrow
+constexpr int PARK_LONG_MIN_TRIPS = 10; // a long document is handed over only while at least this many trips are left
 constexpr int PARK_CTRS = 32;   // ints: list lengths [0, 16) and queue heads [16, 32)
 
 // list a parked document joins: by stage (live topics) and length
 __device__ __forceinline__ int park_list_index(int nlive, int n) {
+    if (n > 192) return 9;
     if (nlive > 16) return 8;
     if (nlive > 8) return n <= 24 ? 0 : n <= 48 ? 1 : n <= 96 ? 2 : 7;
     return n <= 24 ? 3 : n <= 48 ? 4 : n <= 96 ? 5 : 6;

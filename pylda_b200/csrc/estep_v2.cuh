@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) 
         double e[2 * J];
         int it = 0;
         const double tolK = p.tol * (double)K;
+        bool parked = false;
+        const bool long_park = W > 1 && n > 192 && n <= p.park_long;
         while (true) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -276,8 +278,20 @@ __global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) 
             for (int u = 0; u < U; ++u) gamr[u] = gn[u];                 // :188
             ++it;
             dsum = warp_sum(dsum);
+            unsigned bal[U];
             if (W > 1) {
                 if (lane == 0) red[gw] = dsum;
+                if (long_park) {
+                    // live topics of this warp's owners, counted with the same barrier as |d gamma|
+                    int mine = 0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = gt + GT * u;
+                        bal[u] = __ballot_sync(0xffffffffu, k < K && gn[u] != alr[u]);
+                        mine += __popc(bal[u]);
+                    }
+                    if (lane == 0) red[W + gw] = (double)mine;   // (red[W ..) belongs to the ELBO exchange of the final pass)
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int k = gt + GT * u;
@@ -289,6 +303,40 @@ __global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) 
                 for (int w = 0; w < W; ++w) dsum += red[w];
             }
             if (dsum <= tolK || it >= p.max_iter) break;                 // :189-190 / :174
+            if (long_park) {
+                // At most 32 topics alive (gamma_k != alpha_k) and enough trips left: estep_longc finishes the
+                // document on a compact tile (same hand-over as in estep_stream below).
+                int nlive = 0, rank = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const int c = (int)red[W + w];
+                    nlive += c;
+                    if (w < gw) rank += c;
+                }
+                if (nlive >= 1 && nlive <= 32 && it + PARK_LONG_MIN_TRIPS <= p.max_iter) {
+                    int* rec = p.park_rec + (size_t)d * PARK_REC;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = gt + GT * u;
+                        if (k < K) p.gamma[(size_t)d * K + k] = gamr[u];       // final for every dead topic
+                        if ((bal[u] >> lane) & 1u) {
+                            const int slot = rank + __popc(bal[u] & ((1u << lane) - 1u));
+                            rec[2 + slot] = k;
+                            p.park_gam[(size_t)d * PARK_GAM + slot] = gamr[u];
+                        }
+                        rank += __popc(bal[u]);
+                    }
+                    if (gt == 0) {
+                        rec[0] = it;
+                        rec[1] = nlive;
+                        const int li = park_list_index(nlive, n);
+                        const int slot = atomicAdd(p.park_counts + li, 1);
+                        p.park_lists[(size_t)li * p.park_cap + slot] = d;
+                    }
+                    parked = true;
+                    break;
+                }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) er[u] = en[u];
             if (W == 1) {
@@ -301,6 +349,7 @@ __global__ void __launch_bounds__(V == 1 ? 512 : 256) estep_v2(const EParams p) 
             }
         }
 
+        if (parked) continue;
         // ---- final pass: phi from the LAST e (registers e[], owners' er[]) -------------------
         double lacc = 0.0;
         {
@@ -393,11 +442,15 @@ __device__ __forceinline__ void rows_accum_global(const double* __restrict__ Bt,
     }
 }
 
-// FULL = false: lean instantiation for classes whose documents can neither be handed over to the narrow stages
-// (all longer than 192 terms) nor need chunked staging -- the long documents of the headline config; the extra
-// live state of those two features costs the 128-register kernel spills in its trip loop.
-template <int LK, int J, bool FULL>
+// MODE 0: lean instantiation for classes whose documents can neither be handed over (all longer than 192 terms and
+//         the compact stage for long documents off) nor need chunked staging;
+// MODE 2: hand-over to the narrow stages / estep_longc, no chunked staging;
+// MODE 1: both.  The extra live state of each feature costs the 128-register kernel spills in its trip loop, hence
+// one instantiation per combination in use.
+template <int LK, int J, int MODE>
 __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
+    constexpr bool CHUNK = (MODE == 1);
+    constexpr bool PARK = (MODE >= 1);
     constexpr int W = 8;
     constexpr int LN = 32 / LK;
     constexpr int KPAD = 2 * LK * J;
@@ -450,7 +503,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         // ids and counts live in shared memory, p.nmax rows at a time: a document longer than that (thousands of
         // terms) is walked in chunks that are re-staged every trip -- 12 bytes per row against the 8 K of its B row
         const int cap = p.nmax;                             // multiple of W * LN
-        const int nch = FULL ? (npad + cap - 1) / cap : 1;
+        const int nch = CHUNK ? (npad + cap - 1) / cap : 1;
         // (a macro, not a lambda: by-reference captures put the captured variables on the stack)
 #define PYLDA_STAGE_CHUNK(CH)                                                                          \
         {                                                                                              \
@@ -489,8 +542,10 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
         double e[2 * J];
         int it = 0;
         const double tolK = p.tol * (double)K;
-        // hand-over threshold of this document: 32 live topics for n <= 96, 16 for n <= 192, never above
-        const int park_thr = !FULL ? 0 : (p.park_nc >= 16 && n <= 96) ? 32 : (p.park_nc > 0 && n <= 192) ? p.park_nc : 0;
+        // hand-over threshold of this document: 32 live topics for n <= 96, 16 for n <= 192; documents longer than
+        // that: estep_longc at 32 live topics.  (Recomputed where it is used: one value less to keep across the row loop.)
+#define PYLDA_PARK_THR() ((p.park_nc >= 16 && n <= 96) ? 32 : (p.park_nc > 0 && n <= 192) ? p.park_nc \
+                                                            : (n > 192 && n <= p.park_long) ? 32 : 0)
         bool parked = false;
         while (true) {
 #pragma unroll
@@ -574,6 +629,18 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
             ++it;
             dsum = warp_sum(dsum);
             if (lane == 0) red[gw] = dsum;
+            // live topics (gamma_k != alpha_k) of this warp's owners: counted with the same barrier as |d gamma|
+            unsigned bal[U];
+            if (PARK && PYLDA_PARK_THR() > 0) {
+                int mine = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int k = gt + GT * u;
+                    bal[u] = __ballot_sync(0xffffffffu, k < K && gn[u] != alr[u]);
+                    mine += __popc(bal[u]);
+                }
+                if (lane == 0) red[W + gw] = (double)mine;      // (red[W ..) belongs to the ELBO exchange of the final pass)
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = gt + GT * u;
@@ -584,19 +651,12 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
 #pragma unroll
             for (int w = 0; w < W; ++w) dsum += red[w];
             if (dsum <= tolK || it >= p.max_iter) break;                  // :189-190 / :174
-            if (FULL && park_thr > 0) {
-                // Few enough topics alive (gamma_k != alpha_k): the narrow stages (estep_narrow.cuh) finish the
-                // document.  This kernel has no compact stage of its own, so it hands over at 32 live topics already.
-                unsigned bal[U];
-                int mine = 0;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int k = gt + GT * u;
-                    bal[u] = __ballot_sync(0xffffffffu, k < K && gn[u] != alr[u]);
-                    mine += __popc(bal[u]);
-                }
-                if (lane == 0) red[W + gw] = (double)mine;      // (red[W ..) belongs to the ELBO exchange of the final pass)
-                __syncthreads();
+            if (PARK && PYLDA_PARK_THR() > 0) {
+                const int park_thr = PYLDA_PARK_THR();
+                // Few enough topics alive: the narrow stages (estep_narrow.cuh; documents of up to 192 terms) or the
+                // compact stage for long documents (estep_longc.cuh) finish the document.  This kernel has no compact
+                // stage of its own, so it hands over at 32 live topics already.  A long document is only worth the
+                // hand-over (one gather of its live columns) while enough trips are left.
                 int nlive = 0, rank = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
@@ -604,7 +664,7 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
                     nlive += c;
                     if (w < gw) rank += c;
                 }
-                if (nlive >= 1 && nlive <= park_thr) {
+                if (nlive >= 1 && nlive <= park_thr && (n <= 192 || it + PARK_LONG_MIN_TRIPS <= p.max_iter)) {
                     int* rec = p.park_rec + (size_t)d * PARK_REC;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -627,7 +687,6 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
                     parked = true;
                     break;
                 }
-                __syncthreads();                                 // red[W ..] is reused next trip
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) er[u] = en[u];
@@ -698,5 +757,6 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
 }
 
 #undef PYLDA_STAGE_CHUNK
+#undef PYLDA_PARK_THR
 
 }  // namespace pylda

@@ -65,22 +65,36 @@ __global__ void k_elog_transpose(const double* __restrict__ eta, const double* _
 }
 
 // One warp per word: m_w = max_k Elt, Bt = exp(Elt - m_w); zero the padding column and the
-// word's row of the statistics accumulator (variational_bayes.py:147).
+// word's row of the statistics accumulator (variational_bayes.py:147).  flat_part[block] = sum over the block's
+// words of sum_k Bt[w,k] (fixed order: bit-reproducible) -- how flat the model is across topics, see launch_estep.
 __global__ void k_build_B(const double* __restrict__ Elt, int K, int V, int KP, double* __restrict__ Bt,
-                          double* __restrict__ mw, double* __restrict__ phi) {
+                          double* __restrict__ mw, double* __restrict__ phi, double* __restrict__ flat_part) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double tot = 0.0;
     for (int v = warp; v < V; v += nwarps) {
         const double* row = Elt + (size_t)v * KP;
         double m = -1.0e308;
         for (int k = lane; k < K; k += 32) m = fmax(m, row[k]);
         m = warp_max(m);
+        double sb = 0.0;
         for (int k = lane; k < KP; k += 32) {
-            Bt[(size_t)v * KP + k] = (k < K) ? exp(row[k] - m) : 0.0;
+            const double b = (k < K) ? exp(row[k] - m) : 0.0;
+            Bt[(size_t)v * KP + k] = b;
             phi[(size_t)v * KP + k] = 0.0;
+            sb += b;
         }
+        tot += warp_sum(sb);
         if (lane == 0) mw[v] = m;
+    }
+    __shared__ double wtot[32];
+    if (lane == 0) wtot[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += wtot[w];
+        flat_part[blockIdx.x] = a;
     }
 }
 

@@ -9,7 +9,7 @@ import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylda_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 NCCL_ID_BYTES = 128
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -39,6 +39,7 @@ class Stats(ctypes.Structure):
         ("docs_narrow", ctypes.c_int64),
         ("allreduce_ms", ctypes.c_double),
         ("gamma_rows_early", ctypes.c_int64),
+        ("docs_long_compact", ctypes.c_int64),
     ]
 
     def as_dict(self):

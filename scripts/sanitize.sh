@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer memcheck + racecheck on small E-steps that cover every kernel (register tile, narrow stages,
-# shared-memory tile, streaming with hand-over, hybrid cluster kernel), the device M-step and the top-words sort
+# shared-memory tile, streaming with hand-over, compact stage for long documents, hybrid cluster kernel), the device M-step and the top-words sort
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
 import os, sys, numpy
@@ -28,6 +28,8 @@ for K in (100, 10, 50, 200, 500):
     ctx.estep_resident(0, 30, 1e-6, want_alpha_ss=True)          # resident EM iteration: device M-step, top words
     ctx.mstep_resident(1.0 / V, want_eta=False)
     ctx.top_words(5)
+    st = ctx.estep_resident(0, 50, 1e-6)                         # the model after one M-step: long documents reach estep_longc
+    print("K=%d after the M-step: long-compact %d narrow %d" % (K, st["docs_long_compact"], st["docs_narrow"]), flush=True)
 ctx.close()
 PY
 for tool in memcheck racecheck; do

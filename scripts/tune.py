@@ -22,5 +22,5 @@ st = ctx.estep_resident(0, MAXIT, 1e-6)
 os.environ.pop("PYLDA_PROFILE_CLASSES", None)
 ks = [ctx.estep_resident(0, MAXIT, 1e-6)["kernel_ms"] for _ in range(3)]
 r = ctx.get_results(0, gamma=False, phi=False)
-print("classes=%s D=%d kernel_ms=%.3f (min of 3) trips=%.2f doc_ll=%.10e narrow %d/%d revived %d" % (
-    os.environ.get("PYLDA_CLASSES", "default"), D, min(ks), st["inner_iters"] / D, r["doc_ll"], st["docs_narrow_wide"], st["docs_narrow"], st["revived_docs"]), flush=True)
+print("classes=%s D=%d kernel_ms=%.3f (min of 3) trips=%.2f doc_ll=%.10e narrow %d/%d long-compact %d revived %d" % (
+    os.environ.get("PYLDA_CLASSES", "default"), D, min(ks), st["inner_iters"] / D, r["doc_ll"], st["docs_narrow_wide"], st["docs_narrow"], st["docs_long_compact"], st["revived_docs"]), flush=True)

@@ -269,6 +269,45 @@ def test_page_locked_gamma_buffer(ctx, monkeypatch):
         ctx.unpin(pinned)
 
 
+def test_long_documents_finish_in_the_compact_stage(ctx, monkeypatch):
+    """Documents of more than 192 terms are handed over by estep_stream / estep_v2 once at most 32 topics are alive
+    and finished by estep_longc on a compact tile (shared memory or, for the longest, global scratch).  A corpus
+    drawn from an LDA model with (nearly) its own topics as the model, so that the long documents get there: same
+    gamma, statistics, ELBO and trip counts as the oracle, and as the library with that stage switched off."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    K, V, D = 100, 3000, 160
+    row_ptr, ids, cts = synthetic.lda_corpus(D, V, seed=7)
+    n = numpy.diff(row_ptr)
+    assert (n > 400).sum() >= 3 and ((n > 192) & (n <= 272)).sum() >= 1
+    rng = numpy.random.default_rng(7)
+    topics = rng.gamma(0.05, 1.0, size=(50, V))                        # the generator's first draw: its topics
+    topics /= topics.sum(axis=1, keepdims=True)
+    eta = numpy.concatenate([0.01 + 4000.0 * topics, 0.01 + 0.02 * numpy.random.RandomState(3).rand(K - 50, V)])
+    alpha = numpy.full(K, 1.0 / K)
+    ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6, return_iters=True)
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    out = ctx.estep(0, eta, alpha, 50, 1e-6)
+    it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+    print("stats", out["stats"])
+    assert out["stats"]["docs_long_compact"] >= 5 and out["stats"]["revived_docs"] == 0
+    _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "long compact")
+    assert numpy.array_equal(it, ref["iters"])
+    monkeypatch.setenv("PYLDA_LONGC_SMEM", "0")                        # every tile through the global scratch
+    scr = ctx.estep(0, eta, alpha, 50, 1e-6)
+    assert scr["stats"]["docs_long_compact"] == out["stats"]["docs_long_compact"]
+    assert numpy.array_equal(scr["gamma"], out["gamma"])
+    assert max_rel(scr["phi_ss"], out["phi_ss"], floor=PHI_FLOOR) <= 1e-11
+    monkeypatch.delenv("PYLDA_LONGC_SMEM")
+    monkeypatch.setenv("PYLDA_PARK_LONG", "0")
+    off = ctx.estep(0, eta, alpha, 50, 1e-6)
+    assert off["stats"]["docs_long_compact"] == 0
+    assert max_rel(off["gamma"], out["gamma"]) <= 1e-11
+    assert max_rel(off["phi_ss"], out["phi_ss"], floor=PHI_FLOOR) <= 1e-10
+    assert abs(off["doc_ll"] - out["doc_ll"]) <= 1e-12 * abs(out["doc_ll"])
+    assert numpy.array_equal(ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"], it)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_random_shapes_sweep(ctx, seed):
     """Randomised sweep over the number of topics (every compiled lane shape and owner width), corpus
@@ -330,6 +369,7 @@ def test_dead_topic_elimination_changes_nothing(ctx, monkeypatch):
     full = ctx.estep(0, eta, alpha, 50, 1e-6)
     it_full = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
     monkeypatch.delenv("PYLDA_COMPACT")
+    ctx.estep(0, eta, alpha, 50, 1e-6)                       # (first use allocates the hand-over buffers)
     fast = ctx.estep(0, eta, alpha, 50, 1e-6)
     it_fast = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
     assert fast["stats"]["revived_docs"] == 0
