@@ -560,6 +560,7 @@ int launch_longc(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int nmax, long l
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, 256, smem, 0));
     if (occ < 1) return fail(ctx, "internal: zero occupancy for the long-document compact stage (smem %d)", smem);
+    if (const char* e = getenv("PYLDA_LONGC_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
     const long long grid = std::max<long long>(1, std::min<long long>((long long)ctx->prop.multiProcessorCount * occ, ndocs_max));
     const size_t need = (size_t)grid * scratch_rows;
     if (ctx->longc_rows < need) {

@@ -31,17 +31,47 @@ struct LParams {
     int smem_rows;             // rows of the shared-memory tile (multiple of 64)
 };
 
+// L2 eviction priorities (createpolicy / ld.global.L2::cache_hint): the scratch tiles are re-read every trip and
+// should stay in L2; the rows of the (V, KP) table gathered into them, and the tile on its last pass, should not
+// push them out (measured without the hints: 40 % of the tile bytes came from DRAM, profiles/r2g_longc_*).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldg_hint_v2(const double* ptr, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ldg_hint(const double* ptr, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_hint(double* ptr, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
+}
+
 // RR row groups of one trip on the compact tile: norm_n = T[n,:].e, w_n = c_n / norm_n, s += w_n T[n,:].  A lane
 // holds 8 columns of a row; the RR rows of a lane are independent chains (all their loads are in flight together).
-template <int NC, int RR>
-__device__ __forceinline__ void longc_rows(const double* rowp, const double* cntp, const double (&e)[8], double (&s)[8]) {
+// GLB: the tile is in the global scratch (loads carry the L2 policy `pol`), else in shared memory.
+template <int NC, int RR, bool GLB>
+__device__ __forceinline__ void longc_rows(const double* rowp, const double* cntp, const double (&e)[8], double (&s)[8],
+                                           uint64_t pol) {
     constexpr int CPL = 8, LK = NC / CPL, GS = 8 * (32 / LK);
     double b[RR][CPL], c[RR], part[RR];
 #pragma unroll
     for (int q = 0; q < RR; ++q) {
 #pragma unroll
         for (int i = 0; i < CPL; i += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(rowp + (size_t)q * GS * NC + i);
+            const double2 v = GLB ? ldg_hint_v2(rowp + (size_t)q * GS * NC + i, pol)
+                                  : *reinterpret_cast<const double2*>(rowp + (size_t)q * GS * NC + i);
             b[q][i] = v.x;
             b[q][i + 1] = v.y;
         }
@@ -93,6 +123,7 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
     const double tolK = p.tol * (double)K;
     const int ndocs = *p.count;
     const bool owner = gt < NC;
+    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
 
     double* tile_g = lp.scratch_tile + (size_t)blockIdx.x * lp.scratch_rows * NC;
     double* cs = lp.scratch_cnt + (size_t)blockIdx.x * lp.scratch_rows;
@@ -111,7 +142,8 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
         const int* rec = p.rec + (size_t)d * PARK_REC;
         int it = rec[0];
         const int nlive = rec[1];
-        double* T = (npad <= lp.smem_rows) ? tile_s : tile_g;
+        const bool glb = npad > lp.smem_rows;
+        double* T = glb ? tile_g : tile_s;
 
         // ---- term ids and counts (coalesced), then the compact tile: the live columns of every row, gathered from
         //      the (V, KP) table once; four rows per warp in flight ----
@@ -128,12 +160,15 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int rr = r + q * W;
-                    v[q] = (rr < n && col >= 0) ? p.Bt[(size_t)is[rr] * KP + col] : 0.0;
+                    v[q] = (rr < n && col >= 0) ? ldg_hint(p.Bt + (size_t)is[rr] * KP + col, once) : 0.0;
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int rr = r + q * W;
-                    if (rr < npad) T[(size_t)rr * NC + j] = v[q];
+                    if (rr < npad) {
+                        if (glb) stg_hint(T + (size_t)rr * NC + j, v[q], keep);
+                        else T[(size_t)rr * NC + j] = v[q];
+                    }
                 }
             }
         }
@@ -162,8 +197,13 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
 #pragma unroll
             for (int i = 0; i < CPL; ++i) s[i] = 0.0;
             int m = 0;
-            for (; m + RR <= M; m += RR) longc_rows<NC, RR>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s);
-            for (; m < M; ++m) longc_rows<NC, 1>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s);
+            if (glb) {
+                for (; m + RR <= M; m += RR) longc_rows<NC, RR, true>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
+                for (; m < M; ++m) longc_rows<NC, 1, true>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
+            } else {
+                for (; m + RR <= M; m += RR) longc_rows<NC, RR, false>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
+                for (; m < M; ++m) longc_rows<NC, 1, false>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
+            }
             // column sums: over the row lanes by shuffles, over the warps through shared memory
 #pragma unroll
             for (int o = LK; o < 32; o <<= 1) {
@@ -219,7 +259,7 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
             const double* r0 = rowp + (size_t)m * GS * NC;
 #pragma unroll
             for (int i = 0; i < CPL; i += 2) {
-                const double2 v0 = *reinterpret_cast<const double2*>(r0 + i);
+                const double2 v0 = glb ? ldg_hint_v2(r0 + i, once) : *reinterpret_cast<const double2*>(r0 + i);   // last use
                 b0[i] = v0.x; b0[i + 1] = v0.y;
             }
             const double c0 = cntp[m * GS];
