@@ -545,12 +545,14 @@ int narrow_end(pylda_ctx* ctx, pylda_stats* st, ClassTimer& timer) {
 // Compact stage for long documents (estep_longc.cuh): park list 9, fed by estep_stream and estep_v2.
 int launch_longc(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int nmax, long long ndocs_max, int max_iter, double tol,
                  pylda_stats* st, ClassTimer& timer) {
-    const void* fn = estep_longc_lookup(32);
+    int want_occ = 2;
+    if (const char* e = getenv("PYLDA_LONGC_CTAS")) want_occ = (atoi(e) == 3) ? 3 : 2;
+    const void* fn = estep_longc_lookup(32, want_occ);
     if (!fn) return fail(ctx, "no compact-stage kernel for long documents");
     const int NC = 32, K = ctx->K;
     const int fixed = (NC + 8 * NC + 4 * 8 + 2 + ((K + 1) & ~1)) * (int)sizeof(double);
-    // shared-memory tile: documents of up to smem_rows rows never leave the SM; two CTAs per SM
-    int budget = 96 * 1024;
+    // shared-memory tile: documents of up to smem_rows rows never leave the SM; two (three) CTAs per SM
+    int budget = (want_occ == 3 ? 72 : 96) * 1024;
     if (const char* e = getenv("PYLDA_LONGC_SMEM")) budget = std::max(0, atoi(e)) * 1024;
     int smem_rows = std::max(0, (budget - fixed) / (NC * 8)) / 64 * 64;
     const int scratch_rows = std::min((nmax + 63) / 64 * 64, (pc.long_rows + 63) / 64 * 64);
@@ -575,6 +577,8 @@ int launch_longc(pylda_ctx* ctx, Corpus& cp, const ParkCfg& pc, int nmax, long l
     lp.n = narrow_params(ctx, cp, pc, 9, max_iter, tol);
     lp.scratch_tile = ctx->longc_tile; lp.scratch_cnt = ctx->longc_cnt; lp.scratch_ids = ctx->longc_ids;
     lp.scratch_rows = scratch_rows; lp.smem_rows = smem_rows;
+    lp.mix = 4;
+    if (const char* e = getenv("PYLDA_LONGC_MIX")) lp.mix = std::max(1, atoi(e));
     void* args[] = {&lp};
     timer.begin(ctx->stream, "longc<%d> smem=%d (tile rows %d) scratch rows %d grid=%lld", NC, smem, smem_rows, scratch_rows, grid);
     CK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, (size_t)smem, ctx->stream));

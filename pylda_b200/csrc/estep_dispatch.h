@@ -24,5 +24,5 @@ const void* estep_hy_lookup(int LK, int J, int* rows_per_lane);
 // narrow stages (estep_narrow.cuh): NC = 16 / 8 live columns, G lanes per document
 const void* estep_narrow_lookup(int NC, int G, int RPL, int MINB);
 // compact stage for long documents (estep_longc.cuh): NC = 32 live columns
-const void* estep_longc_lookup(int NC);
+const void* estep_longc_lookup(int NC, int ctas_per_sm);
 }  // namespace pylda

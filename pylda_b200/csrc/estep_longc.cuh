@@ -29,6 +29,8 @@ struct LParams {
     int* scratch_ids;          // per CTA: scratch_rows ints (term ids)
     int scratch_rows;          // capacity of one CTA's scratch (multiple of 64)
     int smem_rows;             // rows of the shared-memory tile (multiple of 64)
+    int mix;                   // every mix-th claim takes the next document from the front of the list, the others from
+                               // its back (1: plain order)
 };
 
 // L2 eviction priorities (createpolicy / ld.global.L2::cache_hint): the scratch tiles are re-read every trip and
@@ -63,15 +65,15 @@ __device__ __forceinline__ void stg_hint(double* ptr, double v, uint64_t pol) {
 // GLB: the tile is in the global scratch (loads carry the L2 policy `pol`), else in shared memory.
 template <int NC, int RR, bool GLB>
 __device__ __forceinline__ void longc_rows(const double* rowp, const double* cntp, const double (&e)[8], double (&s)[8],
-                                           uint64_t pol) {
+                                           uint64_t pol, const int (&po)[4]) {
     constexpr int CPL = 8, LK = NC / CPL, GS = 8 * (32 / LK);
     double b[RR][CPL], c[RR], part[RR];
 #pragma unroll
     for (int q = 0; q < RR; ++q) {
 #pragma unroll
         for (int i = 0; i < CPL; i += 2) {
-            const double2 v = GLB ? ldg_hint_v2(rowp + (size_t)q * GS * NC + i, pol)
-                                  : *reinterpret_cast<const double2*>(rowp + (size_t)q * GS * NC + i);
+            const double2 v = GLB ? ldg_hint_v2(rowp + (size_t)q * GS * NC + po[i >> 1], pol)
+                                  : *reinterpret_cast<const double2*>(rowp + (size_t)q * GS * NC + po[i >> 1]);
             b[q][i] = v.x;
             b[q][i + 1] = v.y;
         }
@@ -100,14 +102,15 @@ __device__ __forceinline__ void longc_rows(const double* rowp, const double* cnt
     }
 }
 
-template <int NC>
-__global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
+// RR row groups in flight per lane; MINB CTAs per SM (register budget 65536 / (256 MINB))
+template <int NC, int RR, int MINB>
+__global__ void __launch_bounds__(256, MINB) estep_longc(const LParams lp) {
     constexpr int W = 8;
     constexpr int CPL = 8;                 // columns per lane
     constexpr int LK = NC / CPL;           // lanes per row
+    static_assert(NC == 32, "the bank swizzle below is written for 16 column pairs per row");
     constexpr int LN = 32 / LK;            // rows per warp step
     constexpr int GS = W * LN;             // rows per CTA step
-    constexpr int RR = 4;                  // row groups in flight per lane
     const NParams& p = lp.n;
     extern __shared__ __align__(16) double lsm[];
     double* es = lsm;                      // [NC] e of the live slots
@@ -122,6 +125,15 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
     const int K = p.K, KP = p.KP;
     const double tolK = p.tol * (double)K;
     const int ndocs = *p.count;
+    // Column layout.  A lane owns the column pairs kl + LK t, t = 0..3 (registers 2t, 2t+1 <-> columns 2 (kl + LK t) + h):
+    // for one t the LK lanes of a row read 64 contiguous bytes.  In a row of odd index the two 64-byte halves of
+    // every 128 bytes are swapped, so that the two rows of a quarter warp hit disjoint shared-memory banks (rows are
+    // 256 bytes apart: without the swap every LDS.128 was a 4-way bank conflict, profiles/r2g_longc_cold_raw.txt).
+    auto lcol = [&](int i) { return 2 * (kl + LK * (i >> 1)) + (i & 1); };                 // register -> logical column
+    auto pcol = [&](int j, int r) { return (((j >> 1) ^ ((r & 1) << 2)) << 1) | (j & 1); };   // logical -> position in row r
+    int po[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) po[t] = 2 * (kl + LK * (t ^ (nl & 1)));
     const bool owner = gt < NC;
     const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
 
@@ -133,8 +145,16 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
         __syncthreads();                                   // the previous document is fully retired
         if (gt == 0) ctl[0] = atomicAdd(p.head, 1);
         __syncthreads();
-        const int idx = ctl[0];
-        if (idx >= ndocs) break;
+        const int claim = ctl[0];
+        if (claim >= ndocs) break;
+        // The list is roughly in descending length (estep_stream works longest-first, the 193..272-term documents of
+        // estep_v2 come last).  Taken in that order, all CTAs would hold their longest tiles at the same time -- 2-3x
+        // the L2 -- so one claim in `mix` takes from the front and the others from the back: a permutation of the list.
+        int idx = claim;
+        if (lp.mix > 1) {
+            const int q = claim / lp.mix;
+            idx = (claim % lp.mix == 0) ? q : ndocs - 1 - (claim - q - 1);
+        }
         const int d = p.list[idx];
         const long long base = p.row_ptr[d];
         const int n = (int)(p.row_ptr[d + 1] - base);
@@ -166,8 +186,9 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
                 for (int q = 0; q < 4; ++q) {
                     const int rr = r + q * W;
                     if (rr < npad) {
-                        if (glb) stg_hint(T + (size_t)rr * NC + j, v[q], keep);
-                        else T[(size_t)rr * NC + j] = v[q];
+                        const int pj = pcol(j, rr);
+                        if (glb) stg_hint(T + (size_t)rr * NC + pj, v[q], keep);
+                        else T[(size_t)rr * NC + pj] = v[q];
                     }
                 }
             }
@@ -183,13 +204,13 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
 
         // ---- remaining trips on the compact tile                  (variational_bayes.py:174-190) ----
         const int M = npad / GS;
-        const double* rowp = T + (size_t)(gw * LN + nl) * NC + kl * CPL;
+        const double* rowp = T + (size_t)(gw * LN + nl) * NC;
         const double* cntp = cs + gw * LN + nl;
         double e[CPL];
         while (true) {
 #pragma unroll
             for (int i = 0; i < CPL; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(es + kl * CPL + i);
+                const double2 v = *reinterpret_cast<const double2*>(es + lcol(i));
                 e[i] = v.x;
                 e[i + 1] = v.y;
             }
@@ -198,11 +219,11 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
             for (int i = 0; i < CPL; ++i) s[i] = 0.0;
             int m = 0;
             if (glb) {
-                for (; m + RR <= M; m += RR) longc_rows<NC, RR, true>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
-                for (; m < M; ++m) longc_rows<NC, 1, true>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
+                for (; m + RR <= M; m += RR) longc_rows<NC, RR, true>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep, po);
+                for (; m < M; ++m) longc_rows<NC, 1, true>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep, po);
             } else {
-                for (; m + RR <= M; m += RR) longc_rows<NC, RR, false>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
-                for (; m < M; ++m) longc_rows<NC, 1, false>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep);
+                for (; m + RR <= M; m += RR) longc_rows<NC, RR, false>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep, po);
+                for (; m < M; ++m) longc_rows<NC, 1, false>(rowp + (size_t)m * GS * NC, cntp + m * GS, e, s, keep, po);
             }
             // column sums: over the row lanes by shuffles, over the warps through shared memory
 #pragma unroll
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
             if (nl == 0) {
 #pragma unroll
                 for (int i = 0; i < CPL; i += 2)
-                    *reinterpret_cast<double2*>(spart + gw * NC + kl * CPL + i) = make_double2(s[i], s[i + 1]);
+                    *reinterpret_cast<double2*>(spart + gw * NC + lcol(i)) = make_double2(s[i], s[i + 1]);
             }
             __syncthreads();
             if (gw == 0) {
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
         double ej[CPL];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-            const int j = kl * CPL + i;
+            const int j = lcol(i);
             cols[i] = (j < nlive) ? rec[2 + j] : -1;
             ej[i] = (cols[i] >= 0) ? e[i] - p.e_dead[cols[i]] : 0.0;
         }
@@ -259,7 +280,8 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
             const double* r0 = rowp + (size_t)m * GS * NC;
 #pragma unroll
             for (int i = 0; i < CPL; i += 2) {
-                const double2 v0 = glb ? ldg_hint_v2(r0 + i, once) : *reinterpret_cast<const double2*>(r0 + i);   // last use
+                const double2 v0 = glb ? ldg_hint_v2(r0 + po[i >> 1], once)
+                                       : *reinterpret_cast<const double2*>(r0 + po[i >> 1]);   // last use
                 b0[i] = v0.x; b0[i + 1] = v0.y;
             }
             const double c0 = cntp[m * GS];
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__(256, 2) estep_longc(const LParams lp) {
             for (int r = gw; r < n; r += W) {
                 // w_n of the last trip again: one row per warp, a lane per compact column
                 double pr = 0.0;
-                for (int j = lane; j < NC; j += 32) pr = fma(T[(size_t)r * NC + j], es[j], pr);
+                for (int j = lane; j < NC; j += 32) pr = fma(T[(size_t)r * NC + pcol(j, r)], es[j], pr);
                 pr = warp_sum(pr);
                 const double c0 = cs[r];
                 const double w0 = c0 * rcp_nr(c0 > 0.0 ? pr : 1.0);

@@ -630,14 +630,12 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
             dsum = warp_sum(dsum);
             if (lane == 0) red[gw] = dsum;
             // live topics (gamma_k != alpha_k) of this warp's owners: counted with the same barrier as |d gamma|
-            unsigned bal[U];
             if (PARK && PYLDA_PARK_THR() > 0) {
                 int mine = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int k = gt + GT * u;
-                    bal[u] = __ballot_sync(0xffffffffu, k < K && gn[u] != alr[u]);
-                    mine += __popc(bal[u]);
+                    mine += __popc(__ballot_sync(0xffffffffu, k < K && gn[u] != alr[u]));
                 }
                 if (lane == 0) red[W + gw] = (double)mine;      // (red[W ..) belongs to the ELBO exchange of the final pass)
             }
@@ -657,25 +655,24 @@ __global__ void __launch_bounds__(256, 2) estep_stream(const EParams p) {
                 // compact stage for long documents (estep_longc.cuh) finish the document.  This kernel has no compact
                 // stage of its own, so it hands over at 32 live topics already.  A long document is only worth the
                 // hand-over (one gather of its live columns) while enough trips are left.
-                int nlive = 0, rank = 0;
+                int nlive = 0;
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    const int c = (int)red[W + w];
-                    nlive += c;
-                    if (w < gw) rank += c;
-                }
+                for (int w = 0; w < W; ++w) nlive += (int)red[W + w];
                 if (nlive >= 1 && nlive <= park_thr && (n <= 192 || it + PARK_LONG_MIN_TRIPS <= p.max_iter)) {
                     int* rec = p.park_rec + (size_t)d * PARK_REC;
+                    int rank = 0;
+                    for (int w = 0; w < gw; ++w) rank += (int)red[W + w];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const int k = gt + GT * u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, k < K && gamr[u] != alr[u]);   // gamr = the new gamma
                         if (k < K) p.gamma[(size_t)d * K + k] = gamr[u];       // final for every dead topic
-                        if ((bal[u] >> lane) & 1u) {
-                            const int slot = rank + __popc(bal[u] & ((1u << lane) - 1u));
+                        if ((bal >> lane) & 1u) {
+                            const int slot = rank + __popc(bal & ((1u << lane) - 1u));
                             rec[2 + slot] = k;
                             p.park_gam[(size_t)d * PARK_GAM + slot] = gamr[u];
                         }
-                        rank += __popc(bal[u]);
+                        rank += __popc(bal);
                     }
                     if (gt == 0) {
                         rec[0] = it;
