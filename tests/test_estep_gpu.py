@@ -299,6 +299,14 @@ def test_long_documents_finish_in_the_compact_stage(ctx, monkeypatch):
     assert numpy.array_equal(scr["gamma"], out["gamma"])
     assert max_rel(scr["phi_ss"], out["phi_ss"], floor=PHI_FLOOR) <= 1e-11
     monkeypatch.delenv("PYLDA_LONGC_SMEM")
+    # the streaming kernel's hand-over is only used for a peaked model (flatness statistic of k_build_B): forced off,
+    # only the shared-memory class hands over -- fewer documents in the compact stage, same results
+    monkeypatch.setenv("PYLDA_FLAT_THRESHOLD", "0")
+    lean = ctx.estep(0, eta, alpha, 50, 1e-6)
+    assert 0 < lean["stats"]["docs_long_compact"] < out["stats"]["docs_long_compact"]
+    assert max_rel(lean["gamma"], out["gamma"]) <= 1e-11
+    assert abs(lean["doc_ll"] - out["doc_ll"]) <= 1e-12 * abs(out["doc_ll"])
+    monkeypatch.delenv("PYLDA_FLAT_THRESHOLD")
     monkeypatch.setenv("PYLDA_PARK_LONG", "0")
     off = ctx.estep(0, eta, alpha, 50, 1e-6)
     assert off["stats"]["docs_long_compact"] == 0
