@@ -316,6 +316,37 @@ def test_long_documents_finish_in_the_compact_stage(ctx, monkeypatch):
     assert numpy.array_equal(ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"], it)
 
 
+@pytest.mark.parametrize("K", [4, 8, 20, 33])
+def test_few_topics_tiny_alpha_every_document_is_handed_over(ctx, K):
+    """K at or below the hand-over thresholds with an alpha small enough for the elimination to be on (alpha =
+    0.004): every document has <= 32 live topics from the first trip on.  Whatever each kernel then does with it
+    (the streaming kernel and estep_v2 hand long documents to estep_longc at once, on a compact tile wider than K;
+    the register-tile kernel only compacts when K > 32), the results are the oracle's.  Cold and peaked models."""
+    from oracle import estep_oracle as O
+    from pylda_b200 import synthetic
+    V = 3000
+    row_ptr, ids, cts = synthetic.lda_corpus(300, V, seed=11, topics=6)
+    n = numpy.diff(row_ptr)
+    assert (n > 192).sum() >= 3 and (n <= 24).sum() >= 3
+    alpha = numpy.full(K, 0.004)
+    rng = numpy.random.default_rng(11)
+    topics = rng.gamma(0.05, 1.0, size=(6, V))
+    topics /= topics.sum(axis=1, keepdims=True)
+    peaked = 0.01 + 3000.0 * topics[numpy.arange(K) % 6] * (1.0 + 0.3 * numpy.random.RandomState(5).rand(K, V))
+    ctx.set_corpus(0, row_ptr, ids, cts)
+    for tag, eta in (("cold", synthetic.initial_eta(K, V, 3)), ("peaked", peaked)):
+        ref = O.e_step(row_ptr, ids, cts, eta, alpha, 50, 1e-6, return_iters=True)
+        out = ctx.estep(0, eta, alpha, 50, 1e-6)
+        it = ctx.get_results(0, gamma=False, phi=False, iters=True)["iters"]
+        print(tag, "K=%d" % K, "stats", out["stats"])
+        _check(out, ref["gamma"], ref["phi_ss"], ref["doc_ll"], "K=%d %s" % (K, tag))
+        assert numpy.mean(it == ref["iters"]) >= 0.98
+        handed = out["stats"]["docs_narrow"] + out["stats"]["docs_narrow_wide"] + out["stats"]["docs_long_compact"]
+        print(tag, "K=%d" % K, "handed over", handed)
+        if K > 32 and tag == "peaked":        # (with K <= 32 the register-tile kernel has no compact stage to hand over from)
+            assert handed > 0
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_random_shapes_sweep(ctx, seed):
     """Randomised sweep over the number of topics (every compiled lane shape and owner width), corpus
